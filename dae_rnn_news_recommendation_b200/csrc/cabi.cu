@@ -1,0 +1,154 @@
+// Error plumbing + batch preparation kernel of libdae_sm100.so.
+#include <cstdarg>
+#include "common.cuh"
+
+namespace dae {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace dae
+
+extern "C" int dae_version(void) { return 100; }
+
+extern "C" int dae_last_error(char* buf, size_t len) {
+  if (!buf || len == 0) return 0;
+  strncpy(buf, dae::g_err, len - 1);
+  buf[len - 1] = 0;
+  return (int)strlen(buf);
+}
+
+namespace dae {
+
+// One CTA. Orders the batch rows by label (bitonic sort in smem), derives class segments and the
+// closed-form batch_all data weights:
+//   w_i = 2(n-1)(B-n) + sum_{c != c_i} n_c(n_c-1),   N_valid = sum_c n_c(n_c-1)(B-n_c)
+// which equal the three axis reductions of the B^3 mask in triplet_loss_utils.py:129 / :111.
+constexpr int kMaxB = 4096;
+
+__global__ void __launch_bounds__(1024) batch_prepare_kernel(
+    const int32_t* __restrict__ perm, int64_t offset, int B, const float* __restrict__ labels_all, int strategy,
+    int32_t* __restrict__ rows_out, float* __restrict__ labels_out, int32_t* seg_lo,
+    int32_t* seg_hi, float* __restrict__ weight_out, double* __restrict__ stats) {
+  __shared__ float keys[kMaxB];
+  __shared__ int vals[kMaxB];
+  __shared__ double red[32];
+  int32_t* lo = seg_lo;  // the outputs double as scan scratch (one CTA: __syncthreads orders global writes)
+  int32_t* hi = seg_hi;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int P = 1;
+  while (P < B) P <<= 1;
+  for (int i = tid; i < P; i += nt) {
+    if (i < B) {
+      const int r = perm ? perm[offset + i] : (int)(offset + i);
+      vals[i] = r;
+      keys[i] = (strategy != DAE_TRIPLET_NONE && labels_all) ? labels_all[r] : 0.0f;
+    } else {
+      vals[i] = 0x7fffffff;
+      keys[i] = __int_as_float(0x7f800000);  // +inf sorts last
+    }
+  }
+  __syncthreads();
+  if (strategy != DAE_TRIPLET_NONE) {
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P; i += nt) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float ka = keys[i], kb = keys[ixj];
+            const int va = vals[i], vb = vals[ixj];
+            const bool gt = (ka > kb) || (ka == kb && va > vb);
+            const bool up = ((i & k) == 0);
+            if (gt == up) {
+              keys[i] = kb; keys[ixj] = ka;
+              vals[i] = vb; vals[ixj] = va;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // segment starts / ends
+  for (int i = tid; i < B; i += nt) {
+    lo[i] = (i == 0 || keys[i] != keys[i - 1]) ? i : 0;
+    hi[i] = (i == B - 1 || keys[i] != keys[i + 1]) ? i + 1 : B;
+  }
+  __syncthreads();
+  for (int d = 1; d < B; d <<= 1) {  // max-scan from the left, min-scan from the right
+    int nl[(kMaxB + 1023) / 1024], nh[(kMaxB + 1023) / 1024];
+    int c = 0;
+    for (int i = tid; i < B; i += nt, ++c) {
+      nl[c] = (i >= d) ? max(lo[i], lo[i - d]) : lo[i];
+      nh[c] = (i + d < B) ? min(hi[i], hi[i + d]) : hi[i];
+    }
+    __syncthreads();
+    c = 0;
+    for (int i = tid; i < B; i += nt, ++c) { lo[i] = nl[c]; hi[i] = nh[c]; }
+    __syncthreads();
+  }
+  double t_part = 0.0, nv_part = 0.0;
+  for (int i = tid; i < B; i += nt) {
+    const double n = (double)(hi[i] - lo[i]);
+    t_part += n - 1.0;
+    nv_part += (n - 1.0) * ((double)B - n);
+  }
+  const double T = block_sum(t_part, red);
+  const double NV = block_sum(nv_part, red);
+  for (int i = tid; i < B; i += nt) {
+    const double n = (double)(hi[i] - lo[i]);
+    rows_out[i] = vals[i];
+    if (labels_out) labels_out[i] = keys[i];
+    if (weight_out) {
+      float w = 1.0f;
+      if (strategy == DAE_TRIPLET_BATCH_ALL) w = (float)(2.0 * (n - 1.0) * ((double)B - n) + T - n * (n - 1.0));
+      if (strategy == DAE_TRIPLET_BATCH_HARD) w = 0.0f;  // filled by dae_triplet_batch_hard
+      weight_out[i] = w;
+    }
+  }
+  if (tid < DAE_STAT_SLOTS) {
+    double v = 0.0;
+    if (tid == DAE_STAT_SUM_W) v = (strategy == DAE_TRIPLET_BATCH_ALL) ? 3.0 * NV : (strategy == DAE_TRIPLET_NONE ? (double)B : 0.0);
+    if (tid == DAE_STAT_N_VALID) v = (strategy == DAE_TRIPLET_BATCH_ALL) ? NV : 0.0;
+    stats[tid] = v;
+  }
+}
+
+// strategy none: keep the permutation order, w = 1, one segment; any B.
+__global__ void batch_rows_kernel(const int32_t* __restrict__ perm, int64_t offset, int B, int32_t* __restrict__ rows_out,
+                                  float* __restrict__ labels_out, int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi,
+                                  float* __restrict__ weight_out, double* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    rows_out[i] = perm ? perm[offset + i] : (int)(offset + i);
+    if (labels_out) labels_out[i] = 0.0f;
+    if (seg_lo) seg_lo[i] = 0;
+    if (seg_hi) seg_hi[i] = B;
+    if (weight_out) weight_out[i] = 1.0f;
+  }
+  if (i < DAE_STAT_SLOTS) stats[i] = (i == DAE_STAT_SUM_W) ? (double)B : 0.0;
+}
+
+}  // namespace dae
+
+extern "C" int dae_batch_prepare(const int32_t* perm, int64_t offset, int32_t B, const float* labels_all,
+                                 int32_t strategy, int32_t* rows_out, float* labels_out, int32_t* seg_lo,
+                                 int32_t* seg_hi, float* weight_out, double* stats, void* stream) {
+  DAE_REQUIRE(B >= 1 && rows_out && stats, "dae_batch_prepare: bad B or null output");
+  if (strategy == DAE_TRIPLET_NONE) {
+    dae::batch_rows_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, offset, B, rows_out, labels_out, seg_lo,
+                                                                            seg_hi, weight_out, stats);
+    DAE_CHECK_LAUNCH("dae_batch_prepare(none)");
+    return DAE_OK;
+  }
+  DAE_REQUIRE(B <= dae::kMaxB, "dae_batch_prepare: triplet strategies need B <= %d (got %d)", dae::kMaxB, B);
+  DAE_REQUIRE(seg_lo && seg_hi, "dae_batch_prepare: null segment outputs");
+  DAE_REQUIRE(strategy == DAE_TRIPLET_NONE || labels_all, "dae_batch_prepare: labels required for triplet strategies");
+  dae::batch_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(perm, offset, B, labels_all, strategy, rows_out,
+                                                                 labels_out, seg_lo, seg_hi, weight_out, stats);
+  DAE_CHECK_LAUNCH("dae_batch_prepare");
+  return DAE_OK;
+}

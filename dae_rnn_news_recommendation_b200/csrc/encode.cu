@@ -1,0 +1,240 @@
+// K1 (CSR x dense encode forward) and K5 (encode backward) for sm_100a.
+//
+// Reference ops replaced: tf.sparse.matmul(x_corr, W) + bh, f(.) - f(bh)  (autoencoder/autoencoder.py:377,389)
+// and their autodiff (dense F x H dW from sparse_tensor_dense_matmul's adjoint).
+//
+// Layout: one CTA (128 threads) per batch row.  The row's (col,val) pairs are staged through shared memory in
+// chunks of 128 with masked (zero) entries compacted away, then every thread gathers its 128-bit slice of W[col,:]
+// with read-only vector loads, several rows of W in flight per thread.  W (20 MB at F=10k,H=500) is L2 resident,
+// so the gather runs at L2 bandwidth; HBM only sees the CSR stream, W once, and the E write.
+#include "common.cuh"
+
+namespace dae {
+
+template <int VW> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<1> { using T = float; };
+
+template <int VW>
+__device__ __forceinline__ void ldg_vec(const float* p, float (&out)[VW]) {
+  if constexpr (VW == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+  else if constexpr (VW == 2) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); out[0] = v.x; out[1] = v.y; }
+  else { out[0] = __ldg(p); }
+}
+
+constexpr int kEncThreads = 128;
+
+// stage up to 128 (col,val) pairs of the row into smem, dropping zeros; returns the number kept.
+__device__ __forceinline__ int stage_row_chunk(const int32_t* __restrict__ indices, const float* __restrict__ values,
+                                               int64_t base, int64_t p1, float in_scale, int* s_col, float* s_val,
+                                               int* s_wcnt) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int64_t p = base + tid;
+  float v = 0.0f;
+  int c = 0;
+  if (p < p1) { v = __ldg(values + p) * in_scale; c = __ldg(indices + p); }
+  const bool keep = (v != 0.0f);
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_wcnt[w] = __popc(m);
+  __syncthreads();
+  int off = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < kEncThreads / 32; ++i) { const int n = s_wcnt[i]; if (i < w) off += n; total += n; }
+  if (keep) { const int pos = off + __popc(m & ((1u << lane) - 1u)); s_col[pos] = c; s_val[pos] = v; }
+  __syncthreads();
+  return total;
+}
+
+template <int ACT, int VW, int NC>
+__global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+    const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ W, const float* __restrict__ bh,
+    float* __restrict__ E, int64_t ldE) {
+  __shared__ int s_col[kEncThreads];
+  __shared__ float s_val[kEncThreads];
+  __shared__ int s_wcnt[kEncThreads / 32];
+  const int tid = threadIdx.x;
+  const int r = blockIdx.x;
+  const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
+  const int64_t p0 = indptr[row], p1 = indptr[row + 1];
+
+  float acc[NC][VW];
+  int hcol[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    hcol[c] = (tid + c * kEncThreads) * VW;
+#pragma unroll
+    for (int e = 0; e < VW; ++e) acc[c][e] = 0.0f;
+  }
+
+  for (int64_t base = p0; base < p1; base += kEncThreads) {
+    const int total = stage_row_chunk(indices, values, base, p1, in_scale, s_col, s_val, s_wcnt);
+#pragma unroll 4
+    for (int q = 0; q < total; ++q) {
+      const float v = s_val[q];
+      const float* wrow = W + (int64_t)s_col[q] * H;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (hcol[c] < H) {
+          float w[VW];
+          ldg_vec<VW>(wrow + hcol[c], w);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) acc[c][e] = fmaf(v, w[e], acc[c][e]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (hcol[c] < H) {
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        const float b = __ldg(bh + hcol[c] + e);
+        E[(int64_t)r * ldE + hcol[c] + e] = act_fwd<ACT>(acc[c][e] + b) - act_fwd<ACT>(b);
+      }
+    }
+  }
+}
+
+// backward: dA = dE * f'(A) (A recovered from E + f(bh)), dbh += dA - f'(bh) dE, dW[col,:] += val * dA
+template <int ACT, int VW, int NC>
+__global__ void __launch_bounds__(kEncThreads) encode_bwd_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+    const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ E, const float* __restrict__ bh,
+    float* __restrict__ dE, int64_t ldE, float* __restrict__ dW, float* __restrict__ dbh) {
+  __shared__ int s_col[kEncThreads];
+  __shared__ float s_val[kEncThreads];
+  __shared__ int s_wcnt[kEncThreads / 32];
+  const int tid = threadIdx.x;
+  const int r = blockIdx.x;
+  const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
+  const int64_t p0 = indptr[row], p1 = indptr[row + 1];
+
+  float dA[NC][VW];
+  int hcol[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    hcol[c] = (tid + c * kEncThreads) * VW;
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      dA[c][e] = 0.0f;
+      const int h = hcol[c] + e;
+      if (hcol[c] < H) {
+        const float b = __ldg(bh + h);
+        const float fb = act_fwd<ACT>(b);
+        const float fa = E[(int64_t)r * ldE + h] + fb;
+        const float de = dE[(int64_t)r * ldE + h];
+        const float da = de * act_grad_from_y<ACT>(fa);
+        dA[c][e] = da;
+        dE[(int64_t)r * ldE + h] = da;
+        atomicAdd(dbh + h, da - act_grad_from_y<ACT>(fb) * de);
+      }
+    }
+  }
+  for (int64_t base = p0; base < p1; base += kEncThreads) {
+    const int total = stage_row_chunk(indices, values, base, p1, in_scale, s_col, s_val, s_wcnt);
+    for (int q = 0; q < total; ++q) {
+      const float v = s_val[q];
+      float* wrow = dW + (int64_t)s_col[q] * H;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (hcol[c] < H) {
+          if constexpr (VW == 4) {
+            atomicAdd(reinterpret_cast<float4*>(wrow + hcol[c]),
+                      make_float4(v * dA[c][0], v * dA[c][1], v * dA[c][2], v * dA[c][3]));
+          } else if constexpr (VW == 2) {
+            atomicAdd(reinterpret_cast<float2*>(wrow + hcol[c]), make_float2(v * dA[c][0], v * dA[c][1]));
+          } else {
+            atomicAdd(wrow + hcol[c], v * dA[c][0]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int ACT, int VW>
+static int launch_fwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
+                         const int32_t* rows, int H, float in_scale, const float* W, const float* bh, float* E, int64_t ldE) {
+  switch (nc) {
+    case 1: encode_fwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
+    case 2: encode_fwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
+    case 4: encode_fwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
+    default: encode_fwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
+  }
+  return 0;
+}
+template <int ACT, int VW>
+static int launch_bwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
+                         const int32_t* rows, int H, float in_scale, const float* E, const float* bh, float* dE, int64_t ldE,
+                         float* dW, float* dbh) {
+  switch (nc) {
+    case 1: encode_bwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
+    case 2: encode_bwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
+    case 4: encode_bwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
+    default: encode_bwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
+  }
+  return 0;
+}
+
+static inline int pick_vw(int H, int64_t ld, const void* p) {
+  if (H % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return 4;
+  if (H % 2 == 0 && ld % 2 == 0 && (reinterpret_cast<uintptr_t>(p) & 7) == 0) return 2;
+  return 1;
+}
+static inline int pick_nc(int H, int vw) {
+  const int need = (H + vw * kEncThreads - 1) / (vw * kEncThreads);
+  if (need <= 1) return 1;
+  if (need <= 2) return 2;
+  if (need <= 4) return 4;
+  if (need <= 8) return 8;
+  return -1;
+}
+
+}  // namespace dae
+
+extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
+                                  int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* W, const float* bh,
+                                  int32_t enc_act, float* E, int64_t ldE, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(indptr && indices && values && W && bh && E, "dae_encode_csr_fwd: null pointer");
+  DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_fwd: bad shape n_rows=%d F=%d H=%d ldE=%lld", n_rows, F, H, (long long)ldE);
+  if (n_rows == 0) return DAE_OK;
+  const int vw = pick_vw(H, H, W);
+  const int nc = pick_nc(H, vw);
+  if (nc < 0) { set_error("dae_encode_csr_fwd: H=%d too large for vector width %d", H, vw); return DAE_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n_rows);
+  DAE_DISPATCH_ACT(enc_act, ACT, {
+    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE);
+    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE);
+    else launch_fwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE);
+  });
+  DAE_CHECK_LAUNCH("dae_encode_csr_fwd");
+  return DAE_OK;
+}
+
+extern "C" int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
+                                  int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* E, const float* bh,
+                                  int32_t enc_act, float* dE, int64_t ldE, float* dW, float* dbh, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(indptr && indices && values && E && bh && dE && dW && dbh, "dae_encode_csr_bwd: null pointer");
+  DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  DAE_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * H, st));
+  if (n_rows == 0) return DAE_OK;
+  const int vw = pick_vw(H, H, dW);
+  const int nc = pick_nc(H, vw);
+  if (nc < 0) { set_error("dae_encode_csr_bwd: H=%d too large", H); return DAE_ERR_UNSUPPORTED; }
+  dim3 grid(n_rows);
+  DAE_DISPATCH_ACT(enc_act, ACT, {
+    if (vw == 4) launch_bwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
+    else if (vw == 2) launch_bwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
+    else launch_bwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
+  });
+  DAE_CHECK_LAUNCH("dae_encode_csr_bwd");
+  return DAE_OK;
+}

@@ -1,0 +1,342 @@
+// K4: online triplet mining on the Gram matrix S = E.E^T -- loss, statistics and G = dL_tri/dS, fused, with no
+// B^3 storage.
+//
+// Reference ops replaced: the B x B x B broadcast / mask / softplus / reduce chain of batch_all_triplet_loss
+// (autoencoder/triplet_loss_utils.py:96-131) and the row reductions of batch_hard_triplet_loss (:219-259), plus
+// their autodiff; and the row-wise explicit-triplet loss (autoencoder/autoencoder_triplet.py:308-311).
+//
+// batch_all: rows are label sorted (dae_batch_prepare), so for anchor i the positives are the contiguous segment
+// [lo,hi) \ {i} and the negatives the rest.  One CTA per anchor sweeps the n_pos x n_neg rectangle in registers:
+//   softplus(S_ik - S_ij) = log(1 + u_j v_k),  u_j = exp(m - S_ij), v_k = exp(S_ik - m)   (one FFMA + 2 MUFU per triplet)
+// The sweep is bound by the MUFU pipe (lg2 + rcp per triplet), not by HBM or tensor throughput.
+#include "common.cuh"
+
+namespace dae {
+
+constexpr int kTY = 8, kTX = 32, kTJ = 4, kTK = 8;
+constexpr int kJTile = kTY * kTJ;   // 32 positives per j-tile
+constexpr int kKTile = kTX * kTK;   // 256 negatives per k-tile
+constexpr int kTripThreads = kTY * kTX;
+
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// smem layout (floats): sj[Pj] uj[Pj] gj[Pj] | sk[Pk] vk[Pk] | gk[kTY][Pk]      Pj, Pk = padded counts
+template <bool FAST>
+__global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const float* __restrict__ S, int64_t lds, int B,
+                                                                         const int32_t* __restrict__ seg_lo,
+                                                                         const int32_t* __restrict__ seg_hi, float* __restrict__ G,
+                                                                         int64_t ldg, double* __restrict__ stats, int Pj_max, int Pk_max) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_f[32];
+  __shared__ double red_d[32];
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int lo = seg_lo[i], hi = seg_hi[i];
+  const int nj = hi - lo;       // segment length (includes the anchor itself, neutralised with u = 0)
+  const int nk = B - nj;        // negatives
+  const float* srow = S + (int64_t)i * lds;
+  float* grow = G + (int64_t)i * ldg;
+
+  // row range decides the fast (factorised exp) or the slow (direct, overflow-safe) path
+  float mx = -3.0e38f, mn = 3.0e38f;
+  for (int c = tid; c < B; c += kTripThreads) { const float s = srow[c]; mx = fmaxf(mx, s); mn = fminf(mn, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); }
+  if (tx == 0) { red_f[ty] = mx; red_f[8 + ty] = mn; }
+  __syncthreads();
+  mx = red_f[0]; mn = red_f[8];
+#pragma unroll
+  for (int w = 1; w < kTY; ++w) { mx = fmaxf(mx, red_f[w]); mn = fminf(mn, red_f[8 + w]); }
+  const bool fast_ok = (mx - mn) < 80.0f;
+  if (FAST != fast_ok) return;  // the other instantiation's launch handles this row
+  const float mid = 0.5f * (mx + mn);
+
+  const int Pj = (nj + kJTile - 1) / kJTile * kJTile;
+  const int Pk = (nk + kKTile - 1) / kKTile * kKTile;
+  float* sj = smem;
+  float* uj = sj + Pj_max;
+  float* gj = uj + Pj_max;
+  float* sk = gj + Pj_max;
+  float* vk = sk + Pk_max;
+  float* gk = vk + Pk_max;  // [kTY][Pk_max]
+
+  if (nj <= 1 || nk == 0) {  // no valid triplet with this anchor
+    for (int c = tid; c < B; c += kTripThreads) grow[c] = 0.0f;
+    return;
+  }
+  for (int p = tid; p < Pj; p += kTripThreads) {
+    const int c = lo + p;
+    const bool ok = (p < nj) && (c != i);
+    const float s = ok ? srow[c] : 3.0e38f;               // +huge: never "positive", contributes 0
+    sj[p] = s;
+    uj[p] = ok ? fast_ex2((mid - s) * kLog2e) : 0.0f;
+    gj[p] = 0.0f;
+  }
+  for (int q = tid; q < Pk; q += kTripThreads) {
+    const int c = (q < lo) ? q : q + nj;
+    const bool ok = q < nk;
+    const float s = ok ? srow[c] : -3.0e38f;
+    sk[q] = s;
+    vk[q] = ok ? fast_ex2((s - mid) * kLog2e) : 0.0f;
+  }
+  for (int e = tid; e < kTY * Pk; e += kTripThreads) gk[(e / Pk) * Pk_max + (e % Pk)] = 0.0f;
+  __syncthreads();
+
+  float lacc = 0.0f;
+  int npos = 0;
+  for (int jt = 0; jt < Pj; jt += kJTile) {
+    float s_j[kTJ], u_j[kTJ], rs[kTJ];
+#pragma unroll
+    for (int a = 0; a < kTJ; ++a) { s_j[a] = sj[jt + ty * kTJ + a]; u_j[a] = uj[jt + ty * kTJ + a]; rs[a] = 0.0f; }
+    for (int kt = 0; kt < Pk; kt += kKTile) {
+      float s_k[kTK], v_k[kTK], cs[kTK];
+      const int q0 = kt + tx * kTK;
+#pragma unroll
+      for (int b = 0; b < kTK; b += 4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(sk + q0 + b);
+        const float4 v4 = *reinterpret_cast<const float4*>(vk + q0 + b);
+        s_k[b] = s4.x; s_k[b + 1] = s4.y; s_k[b + 2] = s4.z; s_k[b + 3] = s4.w;
+        v_k[b] = v4.x; v_k[b + 1] = v4.y; v_k[b + 2] = v4.z; v_k[b + 3] = v4.w;
+      }
+#pragma unroll
+      for (int b = 0; b < kTK; ++b) cs[b] = 0.0f;
+#pragma unroll
+      for (int a = 0; a < kTJ; ++a) {
+#pragma unroll
+        for (int b = 0; b < kTK; ++b) {
+          const float x = s_k[b] - s_j[a];           // triplet_distance (triplet_loss_utils.py:106)
+          npos += (x > 1e-16f) ? 1 : 0;              // :114
+          float sp, sg;
+          if (FAST) {
+            const float t = fmaf(u_j[a], v_k[b], 1.0f);  // 1 + exp(x)
+            sp = fast_lg2(t);                             // log2(1+e^x); scaled by ln2 at the end
+            sg = 1.0f - fast_rcp(t);                      // sigmoid(x)
+          } else {
+            const bool valid = (s_j[a] < 1.0e38f) && (s_k[b] > -1.0e38f);
+            const float ax = fabsf(x);
+            const float em = fast_ex2(-ax * kLog2e);
+            const float t = 1.0f + em;
+            const float r = fast_rcp(t);
+            sp = valid ? (fmaxf(x, 0.0f) * kLog2e + fast_lg2(t)) : 0.0f;
+            sg = valid ? (x >= 0.0f ? r : em * r) : 0.0f;
+          }
+          lacc += sp;
+          rs[a] += sg;
+          cs[b] += sg;
+        }
+      }
+      float* g = gk + ty * Pk_max + q0;
+#pragma unroll
+      for (int b = 0; b < kTK; b += 4) {
+        float4 o = *reinterpret_cast<float4*>(g + b);
+        o.x += cs[b]; o.y += cs[b + 1]; o.z += cs[b + 2]; o.w += cs[b + 3];
+        *reinterpret_cast<float4*>(g + b) = o;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kTJ; ++a) {
+      const float t = warp_sum(rs[a]);
+      if (tx == 0) gj[jt + ty * kTJ + a] = t;
+    }
+  }
+  __syncthreads();
+  const float inv = (float)(1.0 / (stats[DAE_STAT_N_VALID] + 1e-16));
+  for (int c = tid; c < B; c += kTripThreads) {
+    float g;
+    if (c >= lo && c < hi) {
+      g = -gj[c - lo] * inv;
+    } else {
+      const int q = (c < lo) ? c : c - nj;
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kTY; ++w) t += gk[w * Pk_max + q];
+      g = t * inv;
+    }
+    grow[c] = g;
+  }
+  const double lsum = block_sum((double)lacc * (double)kLn2, red_d);
+  const double psum = block_sum((double)npos, red_d);
+  if (tid == 0) {
+    atomicAdd(stats + DAE_STAT_TRIPLET_SUM, lsum);
+    atomicAdd(stats + DAE_STAT_NUM, psum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// batch_hard: one CTA per anchor row.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kHardThreads = 256;
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, red[w]);
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kHardThreads) triplet_batch_hard_kernel(const float* __restrict__ S, int64_t lds, int B,
+                                                                          const float* __restrict__ labels, float* __restrict__ G,
+                                                                          int64_t ldg, float* __restrict__ weight,
+                                                                          double* __restrict__ stats) {
+  __shared__ float red[32];
+  __shared__ float redi[32];
+  const int a = blockIdx.x, tid = threadIdx.x;
+  const float* srow = S + (int64_t)a * lds;
+  float* grow = G + (int64_t)a * ldg;
+  const float la = labels[a];
+  // m = row max (triplet_loss_utils.py:227); hn = max(an * S) (:240-243)
+  float m = -3.0e38f, hn = -3.0e38f;
+  for (int c = tid; c < B; c += kHardThreads) {
+    const float s = srow[c];
+    m = fmaxf(m, s);
+    const float an = (labels[c] != la) ? 1.0f : 0.0f;
+    hn = fmaxf(hn, an * s);
+  }
+  m = block_max(m, red);
+  hn = block_max(hn, red);
+  // hp = min(S + m * (1 - ap)) (:228-231)
+  float hpn = -3.0e38f;  // max of the negated values
+  for (int c = tid; c < B; c += kHardThreads) {
+    const float ap = (c != a && labels[c] == la) ? 1.0f : 0.0f;
+    hpn = fmaxf(hpn, -(srow[c] + m * (1.0f - ap)));
+  }
+  const float hp = -block_max(hpn, red);
+  const float td = fmaxf(hn - hp, 0.0f);   // :247
+  const bool active = td > 0.0f;           // :249
+  // tie counts for the reduce_min / reduce_max gradients (TF splits the gradient equally among ties)
+  float tp = 0.0f, tn = 0.0f, tm = 0.0f, tp_masked = 0.0f;
+  for (int c = tid; c < B; c += kHardThreads) {
+    const float s = srow[c];
+    const float ap = (c != a && labels[c] == la) ? 1.0f : 0.0f;
+    const float an = (labels[c] != la) ? 1.0f : 0.0f;
+    if (s + m * (1.0f - ap) == hp) { tp += 1.0f; if (ap == 0.0f) tp_masked += 1.0f; }
+    if (an * s == hn) tn += 1.0f;
+    if (s == m) tm += 1.0f;
+  }
+  tp = block_sum(tp, red);
+  tn = block_sum(tn, redi);
+  tm = block_sum(tm, red);
+  tp_masked = block_sum(tp_masked, redi);
+  // dL/dtd_a (unnormalised by 1/(sum c + eps): applied by triplet_hard_scale_kernel)
+  const float q = active ? 1.0f / (1.0f + expf(-td)) : 0.0f;
+  const float dm = -q * tp_masked / tp;  // gradient reaching the row max through masked argmin entries
+  for (int c = tid; c < B; c += kHardThreads) {
+    const float s = srow[c];
+    const float ap = (c != a && labels[c] == la) ? 1.0f : 0.0f;
+    const float an = (labels[c] != la) ? 1.0f : 0.0f;
+    float g = 0.0f;
+    if (active) {
+      if (s + m * (1.0f - ap) == hp) g -= q / tp;
+      if (an * s == hn) g += an * q / tn;
+      if (s == m) g += dm / tm;
+      // data weight (:251-253): equality is tested on the raw dot products over the whole row
+      float w = 0.0f;
+      if (s == hp) w += 1.0f;
+      if (s == hn) w += 1.0f;
+      if (c == a) w += 1.0f;
+      if (w != 0.0f) atomicAdd(weight + c, w);
+    }
+    grow[c] = g;
+  }
+  if (tid == 0 && active) {
+    atomicAdd(stats + DAE_STAT_TRIPLET_SUM, (double)(fmaxf(td, 0.0f) + log1pf(expf(-td))));  // softplus(td), td > 0
+    atomicAdd(stats + DAE_STAT_N_ACTIVE, 1.0);
+  }
+}
+
+// after all rows: sum_w, and G *= 1/(sum c + eps)
+__global__ void triplet_hard_scale_kernel(float* __restrict__ G, int64_t ldg, int B, const float* __restrict__ weight,
+                                          double* __restrict__ stats) {
+  const float inv = (float)(1.0 / (stats[DAE_STAT_N_ACTIVE] + 1e-16));
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c < B) G[(int64_t)r * ldg + c] *= inv;
+  if (r == 0 && blockIdx.x == 0) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) s += (double)weight[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) stats[DAE_STAT_SUM_W] = s;
+  }
+}
+
+// explicit triplets: one warp per row
+__global__ void triplet_explicit_kernel(const float* __restrict__ E, const float* __restrict__ Ep, const float* __restrict__ En,
+                                        int B, int H, int64_t ld, float alpha, float* __restrict__ dE, float* __restrict__ dEp,
+                                        float* __restrict__ dEn, double* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  const float* e = E + (int64_t)r * ld;
+  const float* ep = Ep + (int64_t)r * ld;
+  const float* en = En + (int64_t)r * ld;
+  float dp = 0.0f;
+  for (int h = lane; h < H; h += 32) dp += e[h] * ep[h] - e[h] * en[h];  // autoencoder_triplet.py:308-311
+  dp = warp_sum(dp);
+  const float x = -dp;                       // loss = softplus(x) = -log_sigmoid(dp)
+  const float sp = fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+  const float sg = 1.0f / (1.0f + expf(-x)); // d softplus / dx
+  const float c = alpha * sg / (float)B;     // d(alpha * mean)/dx
+  for (int h = lane; h < H; h += 32) {
+    const float ev = e[h];
+    dE[(int64_t)r * ld + h] += c * (en[h] - ep[h]);   // accumulated on top of the reconstruction gradient
+    dEp[(int64_t)r * ld + h] += -c * ev;
+    dEn[(int64_t)r * ld + h] += c * ev;
+  }
+  if (lane == 0) atomicAdd(stats + DAE_STAT_TRIPLET_SUM, (double)sp);
+  if (r == 0 && lane == 0) stats[DAE_STAT_N_ACTIVE] = (double)B;
+}
+
+}  // namespace dae
+
+extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, const int32_t* seg_lo, const int32_t* seg_hi, float* G,
+                                     int64_t ldg, double* stats, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(S && seg_lo && seg_hi && G && stats && B >= 1 && B <= 4096 && lds >= B && ldg >= B, "dae_triplet_batch_all: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Pj = (B + kJTile - 1) / kJTile * kJTile;
+  const int Pk = (B + kKTile - 1) / kKTile * kKTile;
+  const size_t smem = sizeof(float) * ((size_t)3 * Pj + (size_t)2 * Pk + (size_t)kTY * Pk);
+  DAE_REQUIRE(smem <= 227 * 1024, "dae_triplet_batch_all: B=%d needs %zu B of shared memory", B, smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  triplet_batch_all_kernel<true><<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
+  triplet_batch_all_kernel<false><<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
+  DAE_CHECK_LAUNCH("dae_triplet_batch_all");
+  return DAE_OK;
+}
+
+extern "C" int dae_triplet_batch_hard(const float* S, int64_t lds, int32_t B, const float* labels, float* G, int64_t ldg,
+                                      float* weight, double* stats, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(S && labels && G && weight && stats && B >= 1 && lds >= B && ldg >= B, "dae_triplet_batch_hard: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DAE_CUDA(cudaMemsetAsync(weight, 0, sizeof(float) * B, st));
+  triplet_batch_hard_kernel<<<B, kHardThreads, 0, st>>>(S, lds, B, labels, G, ldg, weight, stats);
+  dim3 grid((B + 255) / 256, B);
+  triplet_hard_scale_kernel<<<grid, 256, 0, st>>>(G, ldg, B, weight, stats);
+  DAE_CHECK_LAUNCH("dae_triplet_batch_hard");
+  return DAE_OK;
+}
+
+extern "C" int dae_triplet_explicit(const float* E, const float* Ep, const float* En, int32_t B, int32_t H, int64_t ld, float alpha,
+                                    float* dE, float* dEp, float* dEn, double* stats, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(E && Ep && En && dE && dEp && dEn && stats && B >= 1 && H >= 1 && ld >= H, "dae_triplet_explicit: bad arguments");
+  triplet_explicit_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(E, Ep, En, B, H, ld, alpha, dE, dEp, dEn, stats);
+  DAE_CHECK_LAUNCH("dae_triplet_explicit");
+  return DAE_OK;
+}

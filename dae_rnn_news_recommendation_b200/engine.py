@@ -1,0 +1,282 @@
+"""Device-side training/encoding engine: owns the torch buffers and sequences the C-ABI kernels of
+libdae_sm100.so for one training step (the replacement of `tf_session.run([train_step, losses...])`,
+reference autoencoder/autoencoder.py:233,241) and for `transform` (:494-497).
+
+PyTorch is plumbing here (device memory, streams, torch.distributed); every arithmetic op of the hot path is a
+kernel from the library.  There is no CPU path.
+"""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _cabi
+from ._cabi import call, ptr, STAT, STAT_SLOTS
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def canonical_csr(x):
+    """scipy sparse / ndarray -> canonical CSR (sorted, no duplicates), fp32 values, like the feed built by
+    utils.get_sparse_ind_val_shape (autoencoder/utils.py:171-178)."""
+    if isinstance(x, np.ndarray):
+        m = sp.csr_matrix(x)
+    else:
+        m = sp.csr_matrix(x)
+    if not m.has_canonical_format:
+        m = m.copy()
+        m.sum_duplicates()
+    m.sort_indices()
+    return m
+
+
+class DeviceCSR:
+    """CSR matrix resident in HBM: indptr int64[N+1], indices int32[nnz], values fp32[nnz]."""
+
+    def __init__(self, m, device, pin=False):
+        m = canonical_csr(m)
+        self.shape = m.shape
+        self.nnz = int(m.nnz)
+        ip = torch.from_numpy(m.indptr.astype(np.int64))
+        ix = torch.from_numpy(m.indices.astype(np.int32))
+        va = torch.from_numpy(m.data.astype(np.float32))
+        if pin:
+            ip, ix, va = ip.pin_memory(), ix.pin_memory(), va.pin_memory()
+        self.h2d_bytes = ip.numel() * 8 + ix.numel() * 4 + va.numel() * 4
+        self.indptr = ip.to(device, non_blocking=True)
+        self.indices = ix.to(device, non_blocking=True)
+        self.values = va.to(device, non_blocking=True)
+
+    @staticmethod
+    def vstack(mats, device):
+        return DeviceCSR(sp.vstack([canonical_csr(m) for m in mats]).tocsr(), device)
+
+
+class TrainEngine:
+    """Flat parameters + per-batch workspaces + the kernel sequence of one step."""
+
+    def __init__(self, n_features, n_components, enc_act_func='sigmoid', dec_act_func='sigmoid',
+                 loss_func='cross_entropy', opt='gradient_descent', learning_rate=0.1, momentum=0.5, alpha=1.0,
+                 triplet_strategy='batch_all', device='cuda:0', process_group=None):
+        _cabi.lib()  # fail loudly if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _cabi.DaeError('no CUDA device: the DAE hot path has no CPU fallback')
+        self.device = torch.device(device)
+        self.F, self.H = int(n_features), int(n_components)
+        self.enc_act = _cabi.act_code(enc_act_func)
+        self.dec_act = _cabi.act_code(dec_act_func)
+        self.loss = _cabi.LOSS[loss_func]
+        self.opt = _cabi.OPT[opt]
+        self.strategy = _cabi.STRATEGY[triplet_strategy]
+        self.lr, self.momentum, self.alpha = float(learning_rate), float(momentum), float(alpha)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        n = self.F * self.H + self.H + self.F
+        self.n_params = n
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.theta = torch.zeros(n, **f32)
+        self.grad = torch.zeros(n, **f32)
+        self.slot1 = torch.full((n,), 0.1 if opt == 'ada_grad' else 0.0, **f32) if opt != 'gradient_descent' else None
+        self.slot2 = torch.zeros(n, **f32) if opt == 'adam' else None
+        self.step_count = 0
+        self.stats = torch.zeros(STAT_SLOTS, dtype=torch.float64, device=self.device)
+        self._ws_B = 0
+        self.in_scale = 1.0  # decay noise folds into the encode kernels (utils.decay_noise, autoencoder/utils.py:147-159)
+        self.launches = 0  # kernels launched by this engine (bench.py reports it)
+
+    # ---- parameter views -----------------------------------------------------------------------------------------
+    @property
+    def W(self):
+        return self.theta[:self.F * self.H].view(self.F, self.H)
+
+    @property
+    def bh(self):
+        return self.theta[self.F * self.H:self.F * self.H + self.H]
+
+    @property
+    def bv(self):
+        return self.theta[self.F * self.H + self.H:]
+
+    def _gW(self):
+        return self.grad[:self.F * self.H]
+
+    def _gbh(self):
+        return self.grad[self.F * self.H:self.F * self.H + self.H]
+
+    def _gbv(self):
+        return self.grad[self.F * self.H + self.H:]
+
+    def set_parameters(self, W, bh=None, bv=None):
+        self.W.copy_(torch.as_tensor(np.asarray(W, dtype=np.float32)))
+        if bh is not None:
+            self.bh.copy_(torch.as_tensor(np.asarray(bh, dtype=np.float32)))
+        if bv is not None:
+            self.bv.copy_(torch.as_tensor(np.asarray(bv, dtype=np.float32)))
+
+    def get_parameters(self):
+        return {'enc_w': self.W.cpu().numpy().copy(), 'enc_b': self.bh.cpu().numpy().copy(),
+                'dec_b': self.bv.cpu().numpy().copy()}
+
+    # ---- workspaces ----------------------------------------------------------------------------------------------
+    def _ensure_ws(self, B):
+        if B <= self._ws_B:
+            return
+        f32 = dict(dtype=torch.float32, device=self.device)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self.E = torch.empty(B, self.H, **f32)
+        self.dE = torch.empty(B, self.H, **f32)
+        self.Z = torch.empty(B, self.F, **f32)
+        self.row_loss = torch.empty(B, **f32)
+        self.weight = torch.empty(B, **f32)
+        self.rows = torch.empty(B, **i32)
+        self.labels_b = torch.empty(B, **f32)
+        self.seg_lo = torch.empty(B, **i32)
+        self.seg_hi = torch.empty(B, **i32)
+        if self.strategy in (1, 2):
+            self.S = torch.empty(B, B, **f32)
+            self.G = torch.empty(B, B, **f32)
+        self._ws_B = B
+
+    # ---- data ----------------------------------------------------------------------------------------------------
+    def set_data(self, csr, values_corrupt=None, labels=None, csr_corrupt=None):
+        """csr: DeviceCSR of the CLEAN training rows (loss target); values_corrupt: fp32[nnz] values of the corrupted
+        copy sharing the same structure (None = uncorrupted); csr_corrupt: a corrupted copy with its OWN structure
+        (salt-and-pepper adds entries); labels: fp32[N] or None."""
+        self.csr = csr
+        self.csr_c = csr if csr_corrupt is None else csr_corrupt
+        self.values_c = self.csr_c.values if values_corrupt is None else values_corrupt
+        self.labels = labels
+
+    def corrupt_masking(self, corr_frac, keep_host=None, seed=0, epoch=0):
+        """Masking noise on the device copy of the values (utils.masking_noise, autoencoder/utils.py:94-115).
+        keep_host: uint8[nnz] host mask (np.random.rand(nnz) >= v) for RNG-stream parity; else Philox on device."""
+        self.csr_c = self.csr
+        if self.values_c is self.csr.values or self.values_c.numel() != self.csr.nnz:
+            self.values_c = torch.empty_like(self.csr.values)
+        keep = None
+        if keep_host is not None:
+            keep = torch.from_numpy(np.ascontiguousarray(keep_host, dtype=np.uint8)).to(self.device, non_blocking=True)
+        call('dae_mask_values', ptr(self.csr.values), ptr(keep), self.csr.nnz, float(corr_frac), int(seed), int(epoch),
+             ptr(self.values_c), _stream())
+        self.launches += 1
+
+    # ---- the GEMM used for the dense contractions (v1: fp32 CUDA-core kernel) ---------------------------------------
+    def _gemm(self, M, N, K, alpha, A, sam, sak, Bm, sbn, sbk, beta, Cm, ldc):
+        call('dae_sgemm', M, N, K, float(alpha), ptr(A), sam, sak, ptr(Bm), sbn, sbk, float(beta), ptr(Cm), ldc, _stream())
+        self.launches += 1
+
+    # ---- one training step -----------------------------------------------------------------------------------------
+    def step(self, perm, offset, B, stats_log_row=None, train=True):
+        """perm: int32 device tensor (epoch permutation) or None (identity); rows perm[offset:offset+B] form the batch.
+        stats_log_row: optional float64[STAT_SLOTS] device view receiving this step's scalars."""
+        F, H, st = self.F, self.H, _stream()
+        self._ensure_ws(B)
+        c = self.csr
+        strat = self.strategy
+        call('dae_batch_prepare', ptr(perm), int(offset), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
+             ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
+        cc = self.csr_c
+        call('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H, self.in_scale,
+             ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
+        self.launches += 2
+        if strat != 0:
+            self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B)  # S = E.E^T
+            if strat == 1:
+                call('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
+                     ptr(self.stats), st)
+                self.launches += 2
+            else:
+                call('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
+                     ptr(self.stats), st)
+                self.launches += 2
+        self._decode_and_backward(B, self.rows, self.weight if strat != 0 else None, train)
+        if strat != 0 and train:  # dE += alpha (G + G^T) E
+            self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H)
+            self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H)
+        self._encode_backward_and_update(B, self.rows, self.weight if strat != 0 else None, strat, stats_log_row, train)
+
+    def evaluate(self, csr, labels, B=None):
+        """Forward-only cost of the whole set fed as ONE batch with x_corr = x, like the reference's validation pass
+        (autoencoder/autoencoder.py:300-309).  Returns the stats dict."""
+        saved = (self.csr, self.csr_c, self.values_c, self.labels, self.in_scale)
+        try:
+            self.set_data(csr, None, labels)
+            self.in_scale = 1.0
+            self.step(None, 0, csr.shape[0] if B is None else B, None, train=False)
+            return self.read_stats()
+        finally:
+            self.csr, self.csr_c, self.values_c, self.labels, self.in_scale = saved
+
+    def _decode_and_backward(self, B, rows, weight, train=True):
+        F, H, st = self.F, self.H, _stream()
+        c = self.csr
+        self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F)  # Z = E.W^T
+        call('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv), self.dec_act,
+             self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
+        call('dae_colsum', ptr(self.Z), B, F, F, ptr(self._gbv()), st)  # dbv
+        self.launches += 3
+        if not train:
+            return
+        self._gemm(F, H, B, 1.0, self.Z, 1, F, self.E, 1, H, 0.0, self._gW(), H)  # dW_dec = dZ^T.E
+        self._gemm(B, H, F, 1.0, self.Z, F, 1, self.W, 1, H, 0.0, self.dE, H)     # dE = dZ.W
+
+    def _encode_backward_and_update(self, B, rows, weight, strat, stats_log_row, train=True):
+        F, H, st = self.F, self.H, _stream()
+        c = self.csr_c
+        if not train:
+            call('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
+                 ptr(stats_log_row), st)
+            self.launches += 1
+            return
+        call('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale, ptr(self.E),
+             ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
+        call('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
+             ptr(stats_log_row), st)
+        self.launches += 3
+        gscale = 1.0
+        if self.world > 1:  # data parallel: ONE all-reduce of the flat [dW | dbh | dbv] buffer per step
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+            gscale = 1.0 / self.world
+        self.step_count += 1
+        call('dae_optimizer_step', ptr(self.theta), ptr(self.grad), ptr(self.slot1), ptr(self.slot2), self.n_params, self.opt,
+             self.lr, self.momentum, gscale, self.step_count, st)
+        self.launches += 1
+
+    # ---- explicit (anchor, pos, neg) triplets: DenoisingAutoencoderTriplet ---------------------------------------------
+    def step_explicit(self, perm, offset, B, n_rows_each, stats_log_row=None):
+        """self.csr holds [org; pos; neg] stacked (3*n_rows_each rows). autoencoder_triplet.py:256-258,286-288,303-314."""
+        H, st = self.H, _stream()
+        B3 = 3 * B
+        self._ensure_ws(B3)
+        idx = perm[offset:offset + B] if perm is not None else torch.arange(offset, offset + B, device=self.device, dtype=torch.int32)
+        self.rows[:B3] = torch.cat([idx, idx + n_rows_each, idx + 2 * n_rows_each])
+        self.stats.zero_()
+        self.stats[STAT['sum_w']] = float(B)  # each of the three reconstruction terms is a mean over B rows
+        c = self.csr_c
+        call('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H, self.in_scale,
+             ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
+        self.launches += 1
+        self._decode_and_backward(B3, self.rows, None)
+        E, d = self.E, self.dE
+        call('dae_triplet_explicit', ptr(E[0:B]), ptr(E[B:2 * B]), ptr(E[2 * B:B3]), B, H, H, self.alpha, ptr(d[0:B]),
+             ptr(d[B:2 * B]), ptr(d[2 * B:B3]), ptr(self.stats), st)
+        self.launches += 1
+        self._encode_backward_and_update(B3, self.rows, None, 3, stats_log_row)
+
+    # ---- transform ------------------------------------------------------------------------------------------------------
+    def encode(self, csr, in_scale=1.0, out=None, values=None):
+        """E = f(in_scale * X.W + bh) - f(bh) for every row of csr (autoencoder.py:479-505)."""
+        N = csr.shape[0]
+        if out is None:
+            out = torch.empty(N, self.H, dtype=torch.float32, device=self.device)
+        call('dae_encode_csr_fwd', ptr(csr.indptr), ptr(csr.indices), ptr(csr.values if values is None else values), None, N,
+             self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, _stream())
+        self.launches += 1
+        return out
+
+    def read_stats(self):
+        s = self.stats.cpu().numpy()
+        return {k: float(s[i]) for k, i in STAT.items()}

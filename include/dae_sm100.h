@@ -1,0 +1,170 @@
+/*
+ * dae_sm100.h -- C ABI of libdae_sm100.so: the sm_100a kernels behind
+ * DenoisingAutoencoder.fit / transform (DAE-with-triplet-loss training hot path).
+ *
+ * The reference (louislung/DAE_RNN_News_Recommendation) has NO FFI: its arithmetic is a
+ * TensorFlow-1.12 graph run by `tf.Session.run` (autoencoder/autoencoder.py:233,241).  Each entry
+ * point below replaces the TF ops cited next to it; INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.  All citations are relative to the reference root.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; sizes are element counts
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream
+ *   - return value: 0 = ok, <0 = DAE_ERR_*; dae_last_error() gives the message (thread local)
+ *   - the library owns no persistent device memory; the caller (Python/torch) owns every buffer
+ *   - CSR: indptr int64[N+1], indices int32[nnz] (sorted inside a row), values float32[nnz]
+ *   - parameters: ONE flat fp32 buffer theta = [ W (F x H row-major) | bh (H) | bv (F) ]
+ *     gradients / optimizer slots use the same flat layout
+ *   - activations: 0 = identity ('none'), 1 = sigmoid, 2 = tanh      (autoencoder.py:380-387,402-409)
+ *   - losses: 0 = cross_entropy, 1 = mean_squared, 2 = cosine_proximity (triplet_loss_utils.py:268-273)
+ *   - strategies: 0 = none, 1 = batch_all, 2 = batch_hard            (autoencoder.py:70)
+ *   - optimizers: 0 = gradient_descent, 1 = ada_grad, 2 = momentum, 3 = adam (autoencoder.py:451-472)
+ */
+#ifndef DAE_SM100_H
+#define DAE_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAE_OK 0
+#define DAE_ERR_BAD_ARG (-1)
+#define DAE_ERR_CUDA (-2)
+#define DAE_ERR_UNSUPPORTED (-3)
+
+#define DAE_ACT_NONE 0
+#define DAE_ACT_SIGMOID 1
+#define DAE_ACT_TANH 2
+
+#define DAE_LOSS_CE 0
+#define DAE_LOSS_MSE 1
+#define DAE_LOSS_COSINE 2
+
+#define DAE_TRIPLET_NONE 0
+#define DAE_TRIPLET_BATCH_ALL 1
+#define DAE_TRIPLET_BATCH_HARD 2
+
+#define DAE_OPT_SGD 0
+#define DAE_OPT_ADAGRAD 1
+#define DAE_OPT_MOMENTUM 2
+#define DAE_OPT_ADAM 3
+
+/* per-step scalar slots written by the kernels (float64 each), see dae_step_finalize */
+#define DAE_STAT_COST 0
+#define DAE_STAT_AE_LOSS 1
+#define DAE_STAT_TRIPLET_LOSS 2
+#define DAE_STAT_FRACTION 3
+#define DAE_STAT_NUM 4
+#define DAE_STAT_SUM_W 5
+#define DAE_STAT_N_VALID 6
+#define DAE_STAT_SUM_LW 7
+#define DAE_STAT_TRIPLET_SUM 8
+#define DAE_STAT_N_ACTIVE 9
+#define DAE_STAT_SLOTS 16
+
+int dae_version(void);
+/* copies the calling thread's last error message into buf (NUL terminated); returns its length */
+int dae_last_error(char* buf, size_t len);
+
+/* ---- batching -------------------------------------------------------------------------------
+ * Replaces utils.gen_batches' per-batch fancy indexing + get_sparse_ind_val_shape
+ * (autoencoder/utils.py:53-66,162-180) and the label-only parts of batch_all
+ * (triplet_loss_utils.py:47-76,110-111,129): takes rows perm[offset : offset+B] of the epoch's
+ * permutation, orders them by label (the loss is invariant to the order of rows in a batch),
+ * and emits for each batch row its dataset row id, label, class segment [seg_lo, seg_hi) and -
+ * for batch_all - the closed-form data weight w_i and N_valid.  strategy none: order kept, w = 1.
+ * One CTA; B <= 4096.  stats: float64[DAE_STAT_SLOTS], zeroed here, SUM_W / N_VALID filled.
+ */
+int dae_batch_prepare(const int32_t* perm, int64_t offset, int32_t B, const float* labels_all,
+                      int32_t strategy, int32_t* rows_out, float* labels_out, int32_t* seg_lo,
+                      int32_t* seg_hi, float* weight_out, double* stats, void* stream);
+
+/* ---- K1: CSR x dense encode ---------------------------------------------------------------------
+ * E[r,:] = f( in_scale * X[rows[r],:] . W + bh ) - f(bh)      (autoencoder.py:377,389; transform :494-497;
+ * in_scale folds utils.decay_noise, utils.py:147-159).  rows == NULL means rows[r] = r.
+ * E is written fp32 with leading dimension ldE.  Entries whose value is exactly 0 (masked) are skipped.
+ */
+int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const float* values,
+                       const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
+                       const float* W, const float* bh, int32_t enc_act, float* E, int64_t ldE,
+                       void* stream);
+
+/* ---- K5: encode backward -------------------------------------------------------------------------
+ * dA = dE * f'(A);  dbh = sum_i dA_i - f'(bh) * sum_i dE_i;  dW[c,:] += v * dA[r,:] for every stored
+ * (r,c,v) of the corrupted batch (autodiff of autoencoder.py:389).  dE is overwritten with dA.
+ * dW is accumulated with fp32 atomics on top of whatever the decode backward wrote.
+ */
+int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const float* values,
+                       const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
+                       const float* E, const float* bh, int32_t enc_act, float* dE, int64_t ldE,
+                       float* dW, float* dbh, void* stream);
+
+/* ---- fp32 reference GEMM (CUDA cores) ----------------------------------------------------------
+ * C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + beta * C[m,n]; generic strides.
+ * The v1 / validation path for the dense contractions (autoencoder.py:411 and its autodiff,
+ * triplet_loss_utils.py:93,219); the tcgen05 path is dae_gemm_bf16x3_*.
+ */
+int dae_sgemm(int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t sam, int64_t sak,
+              const float* B, int64_t sbn, int64_t sbk, float beta, float* C, int64_t ldc, void* stream);
+
+/* ---- decode loss + dZ (elementwise part of K2) ------------------------------------------------------
+ * In place on Z (B x F, leading dim ldz), where Z = E.W^T (no bias yet):
+ *   D = g(Z + bv); row loss l_i per triplet_loss_utils.py:268-273 against the CLEAN batch rows (CSR,
+ *   densified on the fly); dZ = (w_i / (sum_w + 1e-16)) * dl_i/dD * g'(Z)   (autodiff of :269-275, :411)
+ * Z is overwritten with dZ; row_loss[B] receives l_i.  weight == NULL means w = 1 (strategy none);
+ * sum_w is read from stats[DAE_STAT_SUM_W].
+ */
+int dae_decode_loss_bwd(const int64_t* indptr, const int32_t* indices, const float* values,
+                        const int32_t* rows, int32_t n_rows, int32_t F, const float* bv, int32_t dec_act,
+                        int32_t loss_func, const float* weight, const double* stats, float* Z, int64_t ldz,
+                        float* row_loss, void* stream);
+
+/* column sums: out[f] = sum_r M[r*ld + f]  (dbv = sum_i dZ_i) */
+int dae_colsum(const float* M, int32_t n_rows, int32_t n_cols, int64_t ld, float* out, void* stream);
+
+/* ---- K4: triplet mining -------------------------------------------------------------------------
+ * batch_all (triplet_loss_utils.py:79-131, pos_triplets_only=False as called at autoencoder.py:430):
+ *   rows must be label sorted (dae_batch_prepare). S = E.E^T is an input (B x B, ld lds).
+ *   Writes G (B x B): dL_tri/dS, accumulates loss sum / positive count into stats.
+ * batch_hard (triplet_loss_utils.py:202-259): also writes the data weight (w) and sum_w.
+ */
+int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, const int32_t* seg_lo, const int32_t* seg_hi,
+                          float* G, int64_t ldg, double* stats, void* stream);
+int dae_triplet_batch_hard(const float* S, int64_t lds, int32_t B, const float* labels, float* G, int64_t ldg,
+                           float* weight, double* stats, void* stream);
+/* explicit triplets (autoencoder_triplet.py:308-311): loss = mean softplus(e.en - e.ep); ACCUMULATES alpha * dloss
+ * into dE/dEp/dEn (on top of the reconstruction gradient) and the loss sum into stats[DAE_STAT_TRIPLET_SUM]. */
+int dae_triplet_explicit(const float* E, const float* Ep, const float* En, int32_t B, int32_t H, int64_t ld,
+                         float alpha, float* dE, float* dEp, float* dEn, double* stats, void* stream);
+
+/* ---- step epilogue ---------------------------------------------------------------------------------
+ * Reduces row_loss (x weight) deterministically and fills COST / AE_LOSS / TRIPLET_LOSS / FRACTION / NUM
+ * of `stats` (autoencoder.py:438,441; triplet_loss_utils.py:127,131,257,259,275); then copies the
+ * DAE_STAT_SLOTS doubles to stats_log (one row of the per-epoch log) if non-NULL.
+ */
+int dae_step_finalize(const float* row_loss, const float* weight, int32_t B, int32_t strategy, float alpha,
+                      double* stats, double* stats_log, void* stream);
+
+/* ---- K6: optimizer ------------------------------------------------------------------------------------
+ * theta <- update(theta, grad * grad_scale) over the flat buffer (autoencoder.py:451-472; TF-1.12 rules:
+ * SGD; Adagrad accum(0)=0.1, no eps; Momentum accum=mu*accum+g, theta-=lr*accum; Adam b1 .9 b2 .999 eps 1e-8
+ * with lr_t = lr*sqrt(1-b2^t)/(1-b1^t), t = step (1-based)).
+ */
+int dae_optimizer_step(float* theta, const float* grad, float* slot1, float* slot2, int64_t n, int32_t opt,
+                       float lr, float momentum, float grad_scale, int32_t step, void* stream);
+
+/* ---- corruption -----------------------------------------------------------------------------------------
+ * values_out[p] = keep[p] ? values[p] : 0 where keep is a host-generated byte mask (bit-parity mode with
+ * np.random.rand(nnz) >= v, utils.py:111) -- or, if keep == NULL, a Philox4x32-10 draw keyed by
+ * (seed, epoch, p):  u >= corr_frac  (device mode; same distribution, different stream).
+ */
+int dae_mask_values(const float* values, const uint8_t* keep, int64_t nnz, float corr_frac, uint64_t seed,
+                    uint64_t epoch, float* values_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAE_SM100_H */

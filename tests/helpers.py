@@ -1,0 +1,39 @@
+"""Shared helpers for the parity tests (seeded inputs, tolerances)."""
+import numpy as np
+import scipy.sparse as sp
+
+REL_TOL = 1e-4  # north_star: embeddings and per-step losses within 1e-4 relative of the fp32 oracle
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
+
+
+def random_csr(n, F, nnz_per_row, kind='binary', seed=0):
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        k = int(np.clip(rng.poisson(nnz_per_row), 0 if i % 7 == 3 else 1, F))  # some rows empty
+        c = np.sort(rng.choice(F, size=k, replace=False))
+        rows.append(np.full(k, i))
+        cols.append(c)
+        vals.append(np.ones(k) if kind == 'binary' else rng.random(k) + 0.05)
+    m = sp.csr_matrix((np.concatenate(vals).astype(np.float32), (np.concatenate(rows), np.concatenate(cols))), shape=(n, F))
+    m.sort_indices()
+    return m
+
+
+def mask_csr(m, frac, seed=1):
+    """same structure, a random `frac` of the values zeroed (what masking noise does)"""
+    rng = np.random.default_rng(seed)
+    keep = rng.random(m.nnz) >= frac
+    out = m.copy()
+    out.data = (out.data * keep).astype(np.float32)
+    return out, keep
+
+
+def xavier(F, H, seed=0):
+    b = np.sqrt(6.0 / (F + H))
+    return np.random.default_rng(seed).uniform(-b, b, (F, H)).astype(np.float32)
