@@ -1,0 +1,575 @@
+// tcgen05 / TMA / TMEM GEMM for the dense contractions of the DAE step, fp32-accurate through a 3-pass bf16 split.
+//
+// Reference ops replaced: tf.matmul(encode, tf.transpose(W)) (autoencoder/autoencoder.py:411) and its autodiff
+// (dW = dZ^T.E, dE = dZ.W), and tf.matmul(encode, tf.transpose(encode)) (autoencoder/triplet_loss_utils.py:93,219).
+//
+// Numerics: every fp32 operand x is carried as two bf16 arrays, hi = bf16(x) and lo = bf16(x - hi) (|x - hi - lo| <= 2^-17 |x|).
+//   D += A_hi.B_hi + A_lo.B_hi + A_hi.B_lo      (three kind::f16 MMAs per k-step, fp32 accumulation in TMEM)
+// The dropped lo.lo term is <= 2^-18 relative, so the product is fp32-grade (1e-5 rel. worst case vs the 1e-4 budget).
+//
+// Structure (one CTA per SM, persistent over output tiles; 256 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d, 128B swizzle, into a STAGES-deep smem ring (hi and lo tiles)
+//   warp 1   : MMA issuer     -- one elected lane issues tcgen05.mma (UMMA 128 x BLOCK_N x 16), commits to mbarriers
+//   warp 2   : TMEM allocator -- 512 columns = two BLOCK_N(<=256)-column fp32 accumulator stages
+//   warps 4-7: epilogue       -- tcgen05.ld (lane = output row), fused epilogue, global stores; overlaps the next tile's MMAs
+// Operands may be K-major (K contiguous) or MN-major (M/N contiguous) -- both straight from row-major arrays, so no
+// transposed copies of dZ / E / W are ever made.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace dae {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;    // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kTcThreads = 256;
+constexpr int kAccStages = 2;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
+//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1).
+//   MN-major: 64-element (128 B) column slabs, 8 k-rows per 1024 B group (SBO), next slab LBO bytes further.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int block_n, bool a_mn, bool b_mn) {
+  return (1u << 4)                       // D format f32
+         | (1u << 7) | (1u << 10)        // A, B = bf16
+         | ((a_mn ? 1u : 0u) << 15)      // A major: 0 = K, 1 = MN
+         | ((b_mn ? 1u : 0u) << 16)      // B major
+         | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------------------------------
+struct GemmParams {
+  int M, N, K;           // logical sizes (TMA zero-fills out-of-range rows / columns)
+  int k_splits;          // > 1: split-K
+  int atomic;            // accumulate into C with fp32 atomics (split-K, or C += ...)
+  int a_mn, b_mn;        // operand majorness
+  float alpha;
+  float* C;              // EPI_STORE: fp32 output [M x ldc]
+  int64_t ldc;
+  int n_store;           // columns < n_store are stored
+  int special_col;       // EPI_STORE: this column (the all-ones column of [E | 1]) goes to special_out[m] instead; -1 = none
+  float* special_out;
+  // EPI_DECODE (fused decode loss; M = batch rows, N = features)
+  const int64_t* indptr; const int32_t* indices; const float* values; const int32_t* rows;
+  const float* bv; const float* weight; const double* stats;
+  __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo; int64_t ld_dz;
+  float* row_loss_part;  // [n_tiles_n x M]
+};
+
+enum { EPI_STORE = 0, EPI_DECODE = 1 };
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+                                                                    const __grid_constant__ CUtensorMap tm_a_lo,
+                                                                    const __grid_constant__ CUtensorMap tm_b_hi,
+                                                                    const __grid_constant__ CUtensorMap tm_b_lo,
+                                                                    const GemmParams p) {
+  constexpr int A_TILE = BLOCK_M * BLOCK_K * 2;   // bytes of one bf16 A tile (16 KB)
+  constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[kAccStages], tmem_empty_bar[kAccStages];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_bias[kAccStages][BLOCK_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per_split = (kblocks_total + p.k_splits - 1) / p.k_splits;
+  const int n_work = tiles_m * tiles_n * p.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int mb = w % tiles_m, nb = (w / tiles_m) % tiles_n, ks = w / (tiles_m * tiles_n);
+        const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa_hi = smem + stage * STAGE_BYTES;
+          uint8_t* sa_lo = sa_hi + A_TILE;
+          uint8_t* sb_hi = sa_lo + A_TILE;
+          uint8_t* sb_lo = sb_hi + B_TILE;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi, kb * BLOCK_K, mb * BLOCK_M);
+            tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo, kb * BLOCK_K, mb * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j) {
+              tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi + j * 8192, mb * BLOCK_M + j * 64, kb * BLOCK_K);
+              tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mb * BLOCK_M + j * 64, kb * BLOCK_K);
+            }
+          }
+          if (!p.b_mn) {
+            tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, nb * BLOCK_N);
+            tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, nb * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j) {
+              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int ks = w / (tiles_m * tiles_n);
+        const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_TILE, sb_hi = sa_lo + A_TILE, sb_lo = sb_hi + B_TILE;
+          const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+          const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;  // bytes per UMMA_K
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da_hi = make_desc(sa_hi + k * a_step, a_lbo, 1024);
+            const uint64_t da_lo = make_desc(sa_lo + k * a_step, a_lbo, 1024);
+            const uint64_t db_hi = make_desc(sb_hi + k * b_step, b_lbo, 1024);
+            const uint64_t db_lo = make_desc(sb_lo + k * b_step, b_lbo, 1024);
+            const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+            umma_bf16(tmem_d, da_lo, db_hi, idesc, first);   // small terms first
+            umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
+            umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);                   // frees this smem stage when the MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0) umma_commit(&tmem_full_bar[acc]);    // (empty split: cannot happen with the launcher's splits)
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int ew = warp - 4;                 // TMEM lane quarter
+    const int row_in_tile = ew * 32 + lane;  // accumulator row owned by this thread
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int mb = w % tiles_m, nb = (w / tiles_m) % tiles_n;
+      const int m = mb * BLOCK_M + row_in_tile;
+      const int n0 = nb * BLOCK_N;
+      if (EPI == EPI_DECODE) {  // stage this tile's visible-bias slice (named barrier 1: the 128 epilogue threads)
+        for (int j = threadIdx.x - 128; j < BLOCK_N; j += 128) s_bias[acc][j] = (n0 + j < p.N) ? p.bv[n0 + j] : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+
+      if (EPI == EPI_STORE) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (m < p.M) {
+            float* crow = p.C + (int64_t)m * p.ldc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c * 32 + j;
+              const float v = p.alpha * __uint_as_float(r[j]);
+              if (n == p.special_col) {
+                if (p.atomic) atomicAdd(p.special_out + m, v); else p.special_out[m] = v;
+              } else if (n < p.n_store) {
+                if (p.atomic) atomicAdd(crow + n, v); else crow[n] = v;
+              }
+            }
+          }
+        }
+      } else {
+        // ---- fused decode epilogue: D = g(Z + bv); row loss; dZ -> bf16 hi/lo (autoencoder.py:411, triplet_loss_utils.py:269-275)
+        int64_t pc = 0, pe = 0;
+        int next_col = 0x7fffffff;
+        float sc = 0.0f;
+        if (m < p.M) {
+          const int64_t row = p.rows ? (int64_t)p.rows[m] : (int64_t)m;
+          pc = p.indptr[row]; pe = p.indptr[row + 1];
+          // first stored column >= n0 (columns are sorted inside a row)
+          int64_t lo = pc, hi = pe;
+          while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (p.indices[mid] < n0) lo = mid + 1; else hi = mid; }
+          pc = lo;
+          if (pc < pe) next_col = p.indices[pc];
+          sc = (p.weight ? p.weight[m] : 1.0f) / ((float)p.stats[DAE_STAT_SUM_W] + kEps);
+        }
+        float lsum = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (m < p.M) {
+            uint32_t hi_pk[16], lo_pk[16];
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) {
+              float h2[2], l2[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int j = 2 * j2 + e;
+                const int n = n0 + c * 32 + j;
+                float x = 0.0f;
+                if (n == next_col) {      // densify the clean CSR row on the fly (tf.sparse.to_dense, triplet_loss_utils.py:264)
+                  x = p.values[pc];
+                  ++pc;
+                  next_col = (pc < pe) ? p.indices[pc] : 0x7fffffff;
+                }
+                const float z = __uint_as_float(r[j]) + s_bias[acc][c * 32 + j];
+                const float d = act_fwd<ACT>(z);
+                const float gp = act_grad_from_y<ACT>(d);
+                float dl;
+                if (LOSS == DAE_LOSS_CE) {
+                  const float a = d + kEps, b = (1.0f - d) + kEps;   // :269, evaluated left to right
+                  if (n < p.N) lsum -= x * __logf(a) + (1.0f - x) * __logf(b);
+                  dl = -(x / a - (1.0f - x) / b);
+                } else {
+                  const float e2 = x - d;
+                  if (n < p.N) lsum += e2 * e2;
+                  dl = -2.0f * e2;
+                }
+                const float dz = (n < p.N) ? sc * dl * gp : 0.0f;
+                h2[e] = __bfloat162float(__float2bfloat16_rn(dz));
+                l2[e] = dz - h2[e];
+              }
+              hi_pk[j2] = pack_bf16(h2[0], h2[1]);
+              lo_pk[j2] = pack_bf16(l2[0], l2[1]);
+            }
+            const int ncol = n0 + c * 32;
+            if (ncol < p.ld_dz) {  // ld_dz is a multiple of 32 (launcher), so whole 32-column chunks are in range
+              uint4* dh = reinterpret_cast<uint4*>(p.dz_hi + (int64_t)m * p.ld_dz + ncol);
+              uint4* dl4 = reinterpret_cast<uint4*>(p.dz_lo + (int64_t)m * p.ld_dz + ncol);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                dh[q] = make_uint4(hi_pk[4 * q], hi_pk[4 * q + 1], hi_pk[4 * q + 2], hi_pk[4 * q + 3]);
+                dl4[q] = make_uint4(lo_pk[4 * q], lo_pk[4 * q + 1], lo_pk[4 * q + 2], lo_pk[4 * q + 3]);
+              }
+            }
+          }
+        }
+        if (m < p.M) p.row_loss_part[(int64_t)nb * p.M + m] = lsum;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// fp32 -> (bf16 hi, bf16 lo) split, row by row, zero padding up to ld_dst columns; optional 1.0 in column `ones_col`.
+__global__ void split_bf16_kernel(const float* __restrict__ src, int rows, int cols, int64_t ld_src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int64_t ld_dst, int ones_col, float scale) {
+  const int64_t total = (int64_t)rows * ld_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = (int)(i - r * ld_dst);
+    float v = (c < cols) ? src[r * ld_src + c] * scale : 0.0f;
+    if (c == ones_col) v = 1.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// GG = alpha * (G + G^T) split to bf16 hi/lo (B x ld), for dE_tri = GG . E
+__global__ void sym_split_kernel(const float* __restrict__ G, int B, int64_t ldg, float alpha, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int64_t ld) {
+  __shared__ float t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = bx + j, c = by + tx;            // read G^T tile: G[bx + j][by + tx]
+    t[j][tx] = (r < B && c < B) ? G[(int64_t)r * ldg + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int r = by + j, c = bx + tx;            // output element (r, c) = G[r][c] + G[c][r]
+    if (r < B && c < ld) {
+      float v = 0.0f;
+      if (c < B) v = alpha * (G[(int64_t)r * ldg + c] + t[tx][j]);
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[(int64_t)r * ld + c] = h;
+      lo[(int64_t)r * ld + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [outer x inner] (inner contiguous), row stride ld elements; box = {64, box_outer}, 128B swizzle.
+static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return DAE_ERR_CUDA; }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu", (int)r,
+                                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld); return DAE_ERR_CUDA; }
+  return DAE_OK;
+}
+
+struct Operand { const void* hi; const void* lo; int64_t ld; int mn_major; };
+
+template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
+static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStream_t st) {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  // K-major: tensor [rows=MN x cols=K], box {64 k, tile rows};  MN-major: tensor [rows=K x cols=MN], box {64 mn, 64 k}
+  if (!A.mn_major) {
+    if ((rc = make_map(&ta_hi, A.hi, p.K, p.M, A.ld, BLOCK_M))) return rc;
+    if ((rc = make_map(&ta_lo, A.lo, p.K, p.M, A.ld, BLOCK_M))) return rc;
+  } else {
+    if ((rc = make_map(&ta_hi, A.hi, p.M, p.K, A.ld, 64))) return rc;
+    if ((rc = make_map(&ta_lo, A.lo, p.M, p.K, A.ld, 64))) return rc;
+  }
+  if (!B.mn_major) {
+    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, BLOCK_N))) return rc;
+    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, BLOCK_N))) return rc;
+  } else {
+    if ((rc = make_map(&tb_hi, B.hi, p.N, p.K, B.ld, 64))) return rc;
+    if ((rc = make_map(&tb_lo, B.lo, p.N, p.K, B.ld, 64))) return rc;
+  }
+  p.a_mn = A.mn_major; p.b_mn = B.mn_major;
+  constexpr int smem = STAGES * (2 * BLOCK_M * BLOCK_K * 2 + 2 * BLOCK_N * BLOCK_K * 2) + 1024;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS>;
+  static bool attr = false;
+  if (!attr) { DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.k_splits;
+  int sms = 148;
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, kTcThreads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  return DAE_OK;
+}
+
+}  // namespace dae
+
+using namespace dae;
+
+extern "C" int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo, int64_t ld_dst,
+                              int32_t ones_col, float scale, void* stream) {
+  DAE_REQUIRE(src && hi && lo && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= cols, "dae_split_bf16: bad arguments");
+  const int64_t total = (int64_t)rows * ld_dst;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, ld_src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld_dst,
+                                                              ones_col, scale);
+  DAE_CHECK_LAUNCH("dae_split_bf16");
+  return DAE_OK;
+}
+
+extern "C" int dae_sym_split_bf16(const float* G, int32_t B, int64_t ldg, float alpha, void* hi, void* lo, int64_t ld, void* stream) {
+  DAE_REQUIRE(G && hi && lo && B > 0 && ldg >= B && ld >= B, "dae_sym_split_bf16: bad arguments");
+  dim3 grid((unsigned)((ld + 31) / 32), (B + 31) / 32), block(32, 8);
+  sym_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(G, B, ldg, alpha, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ld);
+  DAE_CHECK_LAUNCH("dae_sym_split_bf16");
+  return DAE_OK;
+}
+
+extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
+                               int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
+                               int64_t ldc, int32_t n_store, int32_t special_col, float* special_out, int32_t k_splits,
+                               int32_t accumulate, void* stream) {
+  DAE_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && M > 0 && N > 0 && K > 0, "dae_gemm_bf16x3: bad arguments");
+  DAE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dae_gemm_bf16x3: operand leading dimensions must be multiples of 8 (TMA 16-byte strides)");
+  DAE_REQUIRE(((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) % 16 == 0, "dae_gemm_bf16x3: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_store <= 0 || n_store > N) n_store = N;
+  if (k_splits < 1) k_splits = 1;
+  const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (k_splits > kblocks) k_splits = kblocks;
+  {  // no empty splits
+    const int per = (kblocks + k_splits - 1) / k_splits;
+    k_splits = (kblocks + per - 1) / per;
+  }
+  if (k_splits > 1 && !accumulate) {
+    DAE_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)n_store * sizeof(float), M, st));
+    if (special_col >= 0 && special_out) DAE_CUDA(cudaMemsetAsync(special_out, 0, sizeof(float) * M, st));
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.k_splits = k_splits; p.atomic = (k_splits > 1 || accumulate) ? 1 : 0; p.alpha = alpha; p.C = C; p.ldc = ldc; p.n_store = n_store;
+  p.special_col = (special_out ? special_col : -1); p.special_out = special_out;
+  Operand A{a_hi, a_lo, lda, a_mn_major}, B{b_hi, b_lo, ldb, b_mn_major};
+  int rc = launch_gemm<256, 2, EPI_STORE, 0, 0>(A, B, p, st);
+  if (rc) return rc;
+  DAE_CHECK_LAUNCH("dae_gemm_bf16x3");
+  return DAE_OK;
+}
+
+extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo, int64_t lde,
+                                       const void* w_hi, const void* w_lo, int64_t ldw, const int64_t* indptr, const int32_t* indices,
+                                       const float* values, const int32_t* rows, const float* bv, int32_t dec_act, int32_t loss_func,
+                                       const float* weight, const double* stats, void* dz_hi, void* dz_lo, int64_t ld_dz,
+                                       float* row_loss_part, void* stream) {
+  DAE_REQUIRE(e_hi && e_lo && w_hi && w_lo && indptr && indices && values && bv && stats && dz_hi && dz_lo && row_loss_part,
+              "dae_decode_fused_bf16x3: null pointer");
+  DAE_REQUIRE(loss_func == DAE_LOSS_CE || loss_func == DAE_LOSS_MSE, "dae_decode_fused_bf16x3: cosine loss uses the unfused path");
+  DAE_REQUIRE(lde % 8 == 0 && ldw % 8 == 0 && ld_dz % 32 == 0 && ld_dz >= F, "dae_decode_fused_bf16x3: bad leading dimensions");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p{};
+  p.M = Brows; p.N = F; p.K = K; p.k_splits = 1; p.alpha = 1.0f; p.special_col = -1;
+  p.indptr = indptr; p.indices = indices; p.values = values; p.rows = rows; p.bv = bv; p.weight = weight; p.stats = stats;
+  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part;
+  Operand A{e_hi, e_lo, lde, 0}, B{w_hi, w_lo, ldw, 0};
+  int rc = 0;
+#define DAE_DEC(ACT, LOSS) rc = launch_gemm<256, 2, EPI_DECODE, ACT, LOSS>(A, B, p, st)
+  if (loss_func == DAE_LOSS_CE) {
+    if (dec_act == DAE_ACT_SIGMOID) DAE_DEC(DAE_ACT_SIGMOID, DAE_LOSS_CE);
+    else if (dec_act == DAE_ACT_TANH) DAE_DEC(DAE_ACT_TANH, DAE_LOSS_CE);
+    else DAE_DEC(DAE_ACT_NONE, DAE_LOSS_CE);
+  } else {
+    if (dec_act == DAE_ACT_SIGMOID) DAE_DEC(DAE_ACT_SIGMOID, DAE_LOSS_MSE);
+    else if (dec_act == DAE_ACT_TANH) DAE_DEC(DAE_ACT_TANH, DAE_LOSS_MSE);
+    else DAE_DEC(DAE_ACT_NONE, DAE_LOSS_MSE);
+  }
+#undef DAE_DEC
+  if (rc) return rc;
+  DAE_CHECK_LAUNCH("dae_decode_fused_bf16x3");
+  return DAE_OK;
+}

@@ -105,6 +105,14 @@ __global__ void colsum_kernel(const float* __restrict__ M, int n_rows, int n_col
   atomicAdd(out + f, (s0 + s1) + (s2 + s3));
 }
 
+__global__ void reduce_parts_kernel(const float* __restrict__ parts, int n_parts, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int p = 0; p < n_parts; ++p) s += parts[(int64_t)p * n + i];
+  out[i] = s;
+}
+
 // Single CTA: deterministic reduction of the weighted row losses + the step's scalars.
 __global__ void __launch_bounds__(1024) step_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ weight,
                                                              int B, int strategy, float alpha, double* __restrict__ stats,
@@ -183,5 +191,13 @@ extern "C" int dae_step_finalize(const float* row_loss, const float* weight, int
   DAE_REQUIRE(row_loss && stats && B >= 1, "dae_step_finalize: bad arguments");
   step_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, weight, B, strategy, alpha, stats, stats_log);
   DAE_CHECK_LAUNCH("dae_step_finalize");
+  return DAE_OK;
+}
+
+extern "C" int dae_reduce_parts(const float* parts, int32_t n_parts, int32_t n, float* out, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(parts && out && n_parts >= 1 && n >= 1, "dae_reduce_parts: bad arguments");
+  reduce_parts_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(parts, n_parts, n, out);
+  DAE_CHECK_LAUNCH("dae_reduce_parts");
   return DAE_OK;
 }

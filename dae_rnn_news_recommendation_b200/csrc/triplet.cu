@@ -306,12 +306,12 @@ extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, con
   const int Pj = (B + kJTile - 1) / kJTile * kJTile;
   const int Pk = (B + kKTile - 1) / kKTile * kKTile;
   const size_t smem = sizeof(float) * ((size_t)3 * Pj + (size_t)2 * Pk + (size_t)kTY * Pk);
-  DAE_REQUIRE(smem <= 227 * 1024, "dae_triplet_batch_all: B=%d needs %zu B of shared memory", B, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  DAE_REQUIRE(smem + 1024 <= 227 * 1024, "dae_triplet_batch_all: B=%d needs %zu B of shared memory", B, smem);
+  static size_t attr_smem = 0;  // opt in to > 48 KB of dynamic shared memory (grown monotonically)
+  if (smem > attr_smem) {
+    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
   triplet_batch_all_kernel<true><<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
   triplet_batch_all_kernel<false><<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);

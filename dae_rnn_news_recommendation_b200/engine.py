@@ -53,6 +53,40 @@ class DeviceCSR:
         return DeviceCSR(sp.vstack([canonical_csr(m) for m in mats]).tocsr(), device)
 
 
+class HostFeed:
+    """One step's inputs packed into ONE pinned host buffer (what `feed_dict` is to the reference's session.run,
+    autoencoder/autoencoder.py:228): [indptr int64 | indices int32 | values f32 | corrupted values f32 | labels f32]."""
+
+    def __init__(self, x_batch, x_corr_values, labels):
+        m = canonical_csr(x_batch)
+        B, nnz = m.shape[0], int(m.nnz)
+        self.B, self.nnz, self.F = B, nnz, m.shape[1]
+
+        def al(n):
+            return (n + 15) // 16 * 16
+        self.off_indptr = 0
+        self.off_indices = al(8 * (B + 1))
+        self.off_values = self.off_indices + al(4 * nnz)
+        self.off_values_c = self.off_values + al(4 * nnz)
+        self.off_labels = self.off_values_c + al(4 * nnz)
+        self.nbytes = self.off_labels + al(4 * B)
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        hb = self.host.numpy()
+        hb[self.off_indptr:self.off_indptr + 8 * (B + 1)] = m.indptr.astype(np.int64).view(np.uint8)
+        hb[self.off_indices:self.off_indices + 4 * nnz] = m.indices.astype(np.int32).view(np.uint8)
+        hb[self.off_values:self.off_values + 4 * nnz] = m.data.astype(np.float32).view(np.uint8)
+        xc = m.data if x_corr_values is None else x_corr_values
+        hb[self.off_values_c:self.off_values_c + 4 * nnz] = np.asarray(xc, dtype=np.float32).view(np.uint8)
+        lab = np.zeros(B, np.float32) if labels is None else np.asarray(labels, dtype=np.float32).reshape(-1)
+        hb[self.off_labels:self.off_labels + 4 * B] = lab.view(np.uint8)
+        self.has_labels = labels is not None
+
+
+class _CSRView:
+    def __init__(self, indptr, indices, values, shape):
+        self.indptr, self.indices, self.values, self.shape, self.nnz = indptr, indices, values, shape, values.numel()
+
+
 class TrainEngine:
     """Flat parameters + per-batch workspaces + the kernel sequence of one step."""
 
@@ -86,6 +120,50 @@ class TrainEngine:
         self._ws_B = 0
         self.in_scale = 1.0  # decay noise folds into the encode kernels (utils.decay_noise, autoencoder/utils.py:147-159)
         self.launches = 0  # kernels launched by this engine (bench.py reports it)
+        self.timed = None  # {kernel name: [(start_event, end_event), ...]} when per-kernel timing is on
+        self._feed_dev = None
+        self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
+
+    # ---- kernel launch plumbing --------------------------------------------------------------------------------------
+    def time_kernels(self, names):
+        """Bracket every launch of the named C-ABI entry points with CUDA events on the launching stream."""
+        self.timed = None if names is None else {n: [] for n in names}
+
+    def kernel_times_ms(self):
+        torch.cuda.synchronize(self.device)
+        return {n: [a.elapsed_time(b) for a, b in ev] for n, ev in (self.timed or {}).items()}
+
+    def _k(self, name, *args, n_launch=1, tag=None):
+        key = tag or name
+        if self.timed is not None and key in self.timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            call(name, *args)
+            b.record()
+            self.timed[key].append((a, b))
+        else:
+            call(name, *args)
+        self.launches += n_launch
+
+    # ---- per-step host feed (the session.run(feed_dict) analog) ---------------------------------------------------------
+    def run_feed(self, feed, stats_log_row=None):
+        """H2D copy of one packed pinned HostFeed, one training step on it, D2H read of the step's scalars."""
+        if self._feed_dev is None or self._feed_dev.numel() < feed.nbytes:
+            self._feed_dev = torch.empty(max(feed.nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        d = self._feed_dev
+        d[:feed.nbytes].copy_(feed.host, non_blocking=True)
+        B, nnz = feed.B, feed.nnz
+        v = lambda off, nb, dt: d[off:off + nb].view(dt)
+        csr = _CSRView(v(feed.off_indptr, 8 * (B + 1), torch.int64), v(feed.off_indices, 4 * nnz, torch.int32),
+                       v(feed.off_values, 4 * nnz, torch.float32), (B, feed.F))
+        self.csr = self.csr_c = csr
+        self.values_c = v(feed.off_values_c, 4 * nnz, torch.float32)
+        self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
+        self.step(None, 0, B, stats_log_row)
+        self._stats_host.copy_(self.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        s = self._stats_host.numpy()
+        return {k: float(s[i]) for k, i in STAT.items()}
 
     # ---- parameter views -----------------------------------------------------------------------------------------
     @property
@@ -159,14 +237,13 @@ class TrainEngine:
         keep = None
         if keep_host is not None:
             keep = torch.from_numpy(np.ascontiguousarray(keep_host, dtype=np.uint8)).to(self.device, non_blocking=True)
-        call('dae_mask_values', ptr(self.csr.values), ptr(keep), self.csr.nnz, float(corr_frac), int(seed), int(epoch),
-             ptr(self.values_c), _stream())
-        self.launches += 1
+        self._k('dae_mask_values', ptr(self.csr.values), ptr(keep), self.csr.nnz, float(corr_frac), int(seed), int(epoch),
+                ptr(self.values_c), _stream())
 
     # ---- the GEMM used for the dense contractions (v1: fp32 CUDA-core kernel) ---------------------------------------
-    def _gemm(self, M, N, K, alpha, A, sam, sak, Bm, sbn, sbk, beta, Cm, ldc):
-        call('dae_sgemm', M, N, K, float(alpha), ptr(A), sam, sak, ptr(Bm), sbn, sbk, float(beta), ptr(Cm), ldc, _stream())
-        self.launches += 1
+    def _gemm(self, M, N, K, alpha, A, sam, sak, Bm, sbn, sbk, beta, Cm, ldc, tag='gemm'):
+        self._k('dae_sgemm', M, N, K, float(alpha), ptr(A), sam, sak, ptr(Bm), sbn, sbk, float(beta), ptr(Cm), ldc, _stream(),
+                tag=tag)
 
     # ---- one training step -----------------------------------------------------------------------------------------
     def step(self, perm, offset, B, stats_log_row=None, train=True):
@@ -174,28 +251,24 @@ class TrainEngine:
         stats_log_row: optional float64[STAT_SLOTS] device view receiving this step's scalars."""
         F, H, st = self.F, self.H, _stream()
         self._ensure_ws(B)
-        c = self.csr
         strat = self.strategy
-        call('dae_batch_prepare', ptr(perm), int(offset), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
-             ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
+        self._k('dae_batch_prepare', ptr(perm), int(offset), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
+                ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
         cc = self.csr_c
-        call('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H, self.in_scale,
-             ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
-        self.launches += 2
+        self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
         if strat != 0:
-            self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B)  # S = E.E^T
+            self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
             if strat == 1:
-                call('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
-                     ptr(self.stats), st)
-                self.launches += 2
+                self._k('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
+                        ptr(self.stats), st, n_launch=2)
             else:
-                call('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
-                     ptr(self.stats), st)
-                self.launches += 2
+                self._k('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
+                        ptr(self.stats), st, n_launch=2)
         self._decode_and_backward(B, self.rows, self.weight if strat != 0 else None, train)
         if strat != 0 and train:  # dE += alpha (G + G^T) E
-            self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H)
-            self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H)
+            self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
+            self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
         self._encode_backward_and_update(B, self.rows, self.weight if strat != 0 else None, strat, stats_log_row, train)
 
     def evaluate(self, csr, labels, B=None):
@@ -213,37 +286,32 @@ class TrainEngine:
     def _decode_and_backward(self, B, rows, weight, train=True):
         F, H, st = self.F, self.H, _stream()
         c = self.csr
-        self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F)  # Z = E.W^T
-        call('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv), self.dec_act,
-             self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
-        call('dae_colsum', ptr(self.Z), B, F, F, ptr(self._gbv()), st)  # dbv
-        self.launches += 3
+        self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F, tag='gemm_decode_fwd')  # Z = E.W^T
+        self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
+                self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
         if not train:
             return
-        self._gemm(F, H, B, 1.0, self.Z, 1, F, self.E, 1, H, 0.0, self._gW(), H)  # dW_dec = dZ^T.E
-        self._gemm(B, H, F, 1.0, self.Z, F, 1, self.W, 1, H, 0.0, self.dE, H)     # dE = dZ.W
+        self._k('dae_colsum', ptr(self.Z), B, F, F, ptr(self._gbv()), st)  # dbv
+        self._gemm(F, H, B, 1.0, self.Z, 1, F, self.E, 1, H, 0.0, self._gW(), H, tag='gemm_decode_dW')  # dW_dec = dZ^T.E
+        self._gemm(B, H, F, 1.0, self.Z, F, 1, self.W, 1, H, 0.0, self.dE, H, tag='gemm_decode_dE')    # dE = dZ.W
 
     def _encode_backward_and_update(self, B, rows, weight, strat, stats_log_row, train=True):
         F, H, st = self.F, self.H, _stream()
         c = self.csr_c
+        if train:
+            self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
+                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
+        self._k('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
+                ptr(stats_log_row), st)
         if not train:
-            call('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
-                 ptr(stats_log_row), st)
-            self.launches += 1
             return
-        call('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale, ptr(self.E),
-             ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
-        call('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
-             ptr(stats_log_row), st)
-        self.launches += 3
         gscale = 1.0
         if self.world > 1:  # data parallel: ONE all-reduce of the flat [dW | dbh | dbv] buffer per step
             torch.distributed.all_reduce(self.grad, group=self.pg)
             gscale = 1.0 / self.world
         self.step_count += 1
-        call('dae_optimizer_step', ptr(self.theta), ptr(self.grad), ptr(self.slot1), ptr(self.slot2), self.n_params, self.opt,
-             self.lr, self.momentum, gscale, self.step_count, st)
-        self.launches += 1
+        self._k('dae_optimizer_step', ptr(self.theta), ptr(self.grad), ptr(self.slot1), ptr(self.slot2), self.n_params,
+                self.opt, self.lr, self.momentum, gscale, self.step_count, st)
 
     # ---- explicit (anchor, pos, neg) triplets: DenoisingAutoencoderTriplet ---------------------------------------------
     def step_explicit(self, perm, offset, B, n_rows_each, stats_log_row=None):
@@ -256,14 +324,12 @@ class TrainEngine:
         self.stats.zero_()
         self.stats[STAT['sum_w']] = float(B)  # each of the three reconstruction terms is a mean over B rows
         c = self.csr_c
-        call('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H, self.in_scale,
-             ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
-        self.launches += 1
+        self._k('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H,
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
         self._decode_and_backward(B3, self.rows, None)
         E, d = self.E, self.dE
-        call('dae_triplet_explicit', ptr(E[0:B]), ptr(E[B:2 * B]), ptr(E[2 * B:B3]), B, H, H, self.alpha, ptr(d[0:B]),
-             ptr(d[B:2 * B]), ptr(d[2 * B:B3]), ptr(self.stats), st)
-        self.launches += 1
+        self._k('dae_triplet_explicit', ptr(E[0:B]), ptr(E[B:2 * B]), ptr(E[2 * B:B3]), B, H, H, self.alpha, ptr(d[0:B]),
+                ptr(d[B:2 * B]), ptr(d[2 * B:B3]), ptr(self.stats), st)
         self._encode_backward_and_update(B3, self.rows, None, 3, stats_log_row)
 
     # ---- transform ------------------------------------------------------------------------------------------------------
@@ -272,9 +338,9 @@ class TrainEngine:
         N = csr.shape[0]
         if out is None:
             out = torch.empty(N, self.H, dtype=torch.float32, device=self.device)
-        call('dae_encode_csr_fwd', ptr(csr.indptr), ptr(csr.indices), ptr(csr.values if values is None else values), None, N,
-             self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, _stream())
-        self.launches += 1
+        self._k('dae_encode_csr_fwd', ptr(csr.indptr), ptr(csr.indices), ptr(csr.values if values is None else values), None,
+                N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, _stream(),
+                tag='encode_transform')
         return out
 
     def read_stats(self):

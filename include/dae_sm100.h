@@ -105,10 +105,45 @@ int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const floa
 /* ---- fp32 reference GEMM (CUDA cores) ----------------------------------------------------------
  * C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + beta * C[m,n]; generic strides.
  * The v1 / validation path for the dense contractions (autoencoder.py:411 and its autodiff,
- * triplet_loss_utils.py:93,219); the tcgen05 path is dae_gemm_bf16x3_*.
+ * triplet_loss_utils.py:93,219); the production path is dae_gemm_bf16x3 / dae_decode_fused_bf16x3.
  */
 int dae_sgemm(int32_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t sam, int64_t sak,
               const float* B, int64_t sbn, int64_t sbk, float beta, float* C, int64_t ldc, void* stream);
+
+/* ---- tcgen05 path for the dense contractions (K2/K3, Gram matrix) -----------------------------------
+ * fp32-accurate GEMM on the 5th-gen tensor cores: each fp32 operand is carried as bf16 hi + bf16 lo
+ * (dae_split_bf16) and D = A_hi.B_hi + A_lo.B_hi + A_hi.B_lo is accumulated in fp32 in TMEM.
+ * TMA-fed (128B swizzle), persistent, warp specialised; operands are read K-major or MN-major straight
+ * from row-major arrays (majorness flags), so dZ^T / E^T / W^T are never materialised.
+ *
+ * dae_split_bf16: hi/lo [rows x ld_dst] <- src [rows x cols] * scale, zero padded; column `ones_col`
+ *   (if >= 0) is set to 1.0 -- the [E | 1] trick that makes dW = dZ^T.[E | 1] also deliver dbv.
+ * dae_sym_split_bf16: hi/lo <- alpha * (G + G^T)   (dE_tri = alpha (G + G^T) E).
+ * dae_gemm_bf16x3: C[m,n] (+)= alpha * sum_k A(m,k) B(n,k).
+ *   a_mn_major = 0: A stored [M x lda] (K contiguous); 1: A stored [K x lda] (M contiguous).  Same for B/N.
+ *   columns n < n_store go to C; column special_col (if special_out != NULL) goes to special_out[m].
+ *   k_splits > 1 or accumulate != 0: fp32 atomics into C (C is zeroed first unless accumulate).
+ * dae_decode_fused_bf16x3: Z = E.W^T with the decode-loss epilogue fused (D = g(Z+bv), CE/MSE row loss
+ *   against the clean CSR rows, dZ written directly as bf16 hi/lo [B x ld_dz]); row_loss_part is
+ *   [ceil(F/256) x B] partial row losses (reduce with dae_reduce_parts).  Replaces autoencoder.py:411 +
+ *   triplet_loss_utils.py:262-275 and their autodiff without materialising Z, D or dense X.
+ */
+int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo,
+                   int64_t ld_dst, int32_t ones_col, float scale, void* stream);
+int dae_sym_split_bf16(const float* G, int32_t B, int64_t ldg, float alpha, void* hi, void* lo, int64_t ld,
+                       void* stream);
+int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo,
+                    int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
+                    int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
+                    float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
+int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
+                            int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
+                            const int64_t* indptr, const int32_t* indices, const float* values,
+                            const int32_t* rows, const float* bv, int32_t dec_act, int32_t loss_func,
+                            const float* weight, const double* stats, void* dz_hi, void* dz_lo,
+                            int64_t ld_dz, float* row_loss_part, void* stream);
+/* out[i] = sum_p parts[p * n + i] (deterministic reduction of the per-tile row-loss partials) */
+int dae_reduce_parts(const float* parts, int32_t n_parts, int32_t n, float* out, void* stream);
 
 /* ---- decode loss + dZ (elementwise part of K2) ------------------------------------------------------
  * In place on Z (B x F, leading dim ldz), where Z = E.W^T (no bias yet):
