@@ -137,30 +137,56 @@ struct GemmParams {
   const int64_t* indptr; const int32_t* indices; const float* values; const int32_t* rows;
   const float* bv; const float* weight; const double* stats;
   __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo; int64_t ld_dz;
-  float* row_loss_part;  // [n_tiles_n x M]
+  float* row_loss_part;  // [2 * n_tiles_n x M] (two column halves per tile)
+  long long* trace;      // optional clock64 trace of CTA 0 (debug)
 };
 
 enum { EPI_STORE = 0, EPI_DECODE = 1 };
+
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kTcThreadsV2 = 128 + 32 * kEpiWarps; // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&v);
 }
+__device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// decoder activation on the MUFU pipe (relative error ~1e-6, inside the 1e-4 parity budget)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float z) {
+  if (ACT == DAE_ACT_SIGMOID) return f_rcp(1.0f + f_ex2(-1.4426950408889634f * z));
+  if (ACT == DAE_ACT_TANH) return 1.0f - 2.0f * f_rcp(1.0f + f_ex2(2.8853900817779268f * z));
+  return z;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 
 template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
-__global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
-                                                                    const __grid_constant__ CUtensorMap tm_a_lo,
-                                                                    const __grid_constant__ CUtensorMap tm_b_hi,
-                                                                    const __grid_constant__ CUtensorMap tm_b_lo,
-                                                                    const GemmParams p) {
+__global__ void __launch_bounds__(kTcThreadsV2, 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+                                                                      const __grid_constant__ CUtensorMap tm_a_lo,
+                                                                      const __grid_constant__ CUtensorMap tm_b_hi,
+                                                                      const __grid_constant__ CUtensorMap tm_b_lo,
+                                                                      const GemmParams p) {
   constexpr int A_TILE = BLOCK_M * BLOCK_K * 2;   // bytes of one bf16 A tile (16 KB)
   constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  constexpr int HALF_N = BLOCK_N / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[kAccStages], tmem_empty_bar[kAccStages];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_bias[kAccStages][BLOCK_N];
+  __shared__ __align__(16) float s_tr[kEpiWarps][32][20];  // per-warp transpose staging for coalesced stores (EPI_STORE)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -230,15 +256,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid
       const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      long long* trace = (blockIdx.x == 0) ? p.trace : nullptr;
+      int tr_i = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int ks = w / (tiles_m * tiles_n);
         const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+        if (trace && tr_i < 500) trace[tr_i++] = clock64();
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
+        if (trace && tr_i < 500) trace[tr_i++] = clock64();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (trace && tr_i < 500) trace[tr_i++] = clock64();
           const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sa_lo = sa_hi + A_TILE, sb_hi = sa_lo + A_TILE, sb_lo = sb_hi + B_TILE;
           const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
@@ -258,46 +289,79 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid
           if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (kb1 <= kb0) umma_commit(&tmem_full_bar[acc]);    // (empty split: cannot happen with the launcher's splits)
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
+      if (trace && tr_i < 500) trace[tr_i++] = clock64();
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
-    const int ew = warp - 4;                 // TMEM lane quarter
-    const int row_in_tile = ew * 32 + lane;  // accumulator row owned by this thread
+    const int ew = warp - 4;
+    const int quarter = ew & 3;              // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = ew >> 2;                // which half of the tile's columns
+    const int row_in_tile = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
+    long long* trace = (blockIdx.x == 0 && ew == 0 && lane == 0) ? p.trace : nullptr;
+    int tr_i = 500;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int mb = w % tiles_m, nb = (w / tiles_m) % tiles_n;
       const int m = mb * BLOCK_M + row_in_tile;
-      const int n0 = nb * BLOCK_N;
-      if (EPI == EPI_DECODE) {  // stage this tile's visible-bias slice (named barrier 1: the 128 epilogue threads)
-        for (int j = threadIdx.x - 128; j < BLOCK_N; j += 128) s_bias[acc][j] = (n0 + j < p.N) ? p.bv[n0 + j] : 0.0f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int n0 = nb * BLOCK_N + half * HALF_N;
+      if (EPI == EPI_DECODE) {  // stage this tile's visible-bias slice (named barrier 1: the epilogue threads)
+        for (int j = threadIdx.x - 128; j < BLOCK_N; j += 32 * kEpiWarps)
+          s_bias[acc][j] = (nb * BLOCK_N + j < p.N) ? p.bv[nb * BLOCK_N + j] : 0.0f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
+      if (trace && tr_i < 1000) trace[tr_i++] = clock64();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+      if (trace && tr_i < 1000) trace[tr_i++] = clock64();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * HALF_N;
 
       if (EPI == EPI_STORE) {
+        float (*tr)[20] = s_tr[ew];
+        const int m_base = mb * BLOCK_M + quarter * 32;
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
+        for (int c = 0; c < HALF_N / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c * 16, r);
           tmem_ld_wait();
-          if (m < p.M) {
-            float* crow = p.C + (int64_t)m * p.ldc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = n0 + c * 32 + j;
-              const float v = p.alpha * __uint_as_float(r[j]);
-              if (n == p.special_col) {
-                if (p.atomic) atomicAdd(p.special_out + m, v); else p.special_out[m] = v;
-              } else if (n < p.n_store) {
-                if (p.atomic) atomicAdd(crow + n, v); else crow[n] = v;
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(&tr[lane][4 * q]) =
+                make_float4(p.alpha * __uint_as_float(r[4 * q]), p.alpha * __uint_as_float(r[4 * q + 1]),
+                            p.alpha * __uint_as_float(r[4 * q + 2]), p.alpha * __uint_as_float(r[4 * q + 3]));
+          __syncwarp();
+          const int nc = n0 + c * 16;   // first column of this 16-wide chunk
+          const bool interior = vec_ok && (m_base + 32 <= p.M) && (nc + 16 <= p.n_store) && (p.special_col < nc || p.special_col >= nc + 16);
+          if (interior) {               // fast path: 8 rows x 64 B per store instruction, 128-bit accesses
+            const int rsub = lane >> 2, c4 = (lane & 3) * 4;
+            float* dst = p.C + (int64_t)(m_base + rsub) * p.ldc + nc + c4;
+            const int64_t step = 8 * p.ldc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 v = *reinterpret_cast<const float4*>(&tr[rsub + 8 * i][c4]);
+              if (p.atomic) atomicAdd(reinterpret_cast<float4*>(dst), v); else *reinterpret_cast<float4*>(dst) = v;
+              dst += step;
+            }
+          } else {                      // edge tiles / the [dW | dbv] column / unaligned C
+            const int rsub = lane >> 4, csub = lane & 15;
+            const int n = nc + csub;
+            for (int i = 0; i < 16; ++i) {
+              const int rr = 2 * i + rsub;
+              const int mm = m_base + rr;
+              const float v = tr[rr][csub];
+              if (mm < p.M) {
+                if (n == p.special_col) {
+                  if (p.atomic) atomicAdd(p.special_out + mm, v); else p.special_out[mm] = v;
+                } else if (n < p.n_store) {
+                  float* dst = p.C + (int64_t)mm * p.ldc + n;
+                  if (p.atomic) atomicAdd(dst, v); else *dst = v;
+                }
               }
             }
           }
+          __syncwarp();
         }
       } else {
         // ---- fused decode epilogue: D = g(Z + bv); row loss; dZ -> bf16 hi/lo (autoencoder.py:411, triplet_loss_utils.py:269-275)
@@ -307,16 +371,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid
         if (m < p.M) {
           const int64_t row = p.rows ? (int64_t)p.rows[m] : (int64_t)m;
           pc = p.indptr[row]; pe = p.indptr[row + 1];
-          // first stored column >= n0 (columns are sorted inside a row)
-          int64_t lo = pc, hi = pe;
+          int64_t lo = pc, hi = pe;   // first stored column >= n0 (columns are sorted inside a row)
           while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (p.indices[mid] < n0) lo = mid + 1; else hi = mid; }
           pc = lo;
           if (pc < pe) next_col = p.indices[pc];
           sc = (p.weight ? p.weight[m] : 1.0f) / ((float)p.stats[DAE_STAT_SUM_W] + kEps);
         }
-        float lsum = 0.0f;
+        float lsum = 0.0f;   // CE: accumulated in log2 units, scaled by ln2 at the end
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = 0; c < HALF_N / 32; ++c) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -329,26 +392,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid
               for (int e = 0; e < 2; ++e) {
                 const int j = 2 * j2 + e;
                 const int n = n0 + c * 32 + j;
-                float x = 0.0f;
-                if (n == next_col) {      // densify the clean CSR row on the fly (tf.sparse.to_dense, triplet_loss_utils.py:264)
-                  x = p.values[pc];
-                  ++pc;
-                  next_col = (pc < pe) ? p.indices[pc] : 0x7fffffff;
-                }
-                const float z = __uint_as_float(r[j]) + s_bias[acc][c * 32 + j];
-                const float d = act_fwd<ACT>(z);
+                const float z = __uint_as_float(r[j]) + s_bias[acc][half * HALF_N + c * 32 + j];
+                const float d = act_fast<ACT>(z);
                 const float gp = act_grad_from_y<ACT>(d);
-                float dl;
+                float dz;
                 if (LOSS == DAE_LOSS_CE) {
-                  const float a = d + kEps, b = (1.0f - d) + kEps;   // :269, evaluated left to right
-                  if (n < p.N) lsum -= x * __logf(a) + (1.0f - x) * __logf(b);
-                  dl = -(x / a - (1.0f - x) / b);
+                  const float omd = 1.0f - d;
+                  const float b = omd + kEps;                 // 1. - decode + 1e-16, left to right (:269)
+                  if (n != next_col) {                        // x == 0 (99 % of the entries)
+                    if (n < p.N) lsum -= f_lg2(b);
+                    // dl * gp = (1/b) * d * omd; omd/b == 1 exactly in fp32 unless omd == 0 (then the product is 0)
+                    dz = (ACT == DAE_ACT_SIGMOID) ? ((omd != 0.0f) ? sc * d : 0.0f) : sc * gp * f_rcp(b);
+                  } else {                                    // densify the clean CSR row on the fly (:264)
+                    const float x = p.values[pc];
+                    ++pc;
+                    next_col = (pc < pe) ? p.indices[pc] : 0x7fffffff;
+                    const float a = d + kEps;
+                    lsum -= x * f_lg2(a) + (1.0f - x) * f_lg2(b);
+                    dz = sc * gp * ((1.0f - x) * f_rcp(b) - x * f_rcp(a));
+                  }
                 } else {
+                  float x = 0.0f;
+                  if (n == next_col) {
+                    x = p.values[pc];
+                    ++pc;
+                    next_col = (pc < pe) ? p.indices[pc] : 0x7fffffff;
+                  }
                   const float e2 = x - d;
                   if (n < p.N) lsum += e2 * e2;
-                  dl = -2.0f * e2;
+                  dz = -2.0f * sc * e2 * gp;
                 }
-                const float dz = (n < p.N) ? sc * dl * gp : 0.0f;
+                if (n >= p.N) dz = 0.0f;
                 h2[e] = __bfloat162float(__float2bfloat16_rn(dz));
                 l2[e] = dz - h2[e];
               }
@@ -367,11 +441,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_bf16x3_kernel(const __grid
             }
           }
         }
-        if (m < p.M) p.row_loss_part[(int64_t)nb * p.M + m] = lsum;
+        if (m < p.M) p.row_loss_part[(int64_t)(nb * 2 + half) * p.M + m] = (LOSS == DAE_LOSS_CE) ? lsum * 0.6931471805599453f : lsum;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (trace && tr_i < 1000) trace[tr_i++] = clock64();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -485,7 +560,7 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.k_splits;
   int sms = 148;
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kTcThreads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  kern<<<grid, kTcThreadsV2, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   return DAE_OK;
 }
 
@@ -512,10 +587,10 @@ extern "C" int dae_sym_split_bf16(const float* G, int32_t B, int64_t ldg, float 
   return DAE_OK;
 }
 
-extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
-                               int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
-                               int64_t ldc, int32_t n_store, int32_t special_col, float* special_out, int32_t k_splits,
-                               int32_t accumulate, void* stream) {
+static int gemm_store_dispatch(int variant, long long* trace, int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi,
+                               const void* a_lo, int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
+                               int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col, float* special_out,
+                               int32_t k_splits, int32_t accumulate, void* stream) {
   DAE_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && M > 0 && N > 0 && K > 0, "dae_gemm_bf16x3: bad arguments");
   DAE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dae_gemm_bf16x3: operand leading dimensions must be multiples of 8 (TMA 16-byte strides)");
   DAE_REQUIRE(((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) % 16 == 0, "dae_gemm_bf16x3: operands must be 16-byte aligned");
@@ -533,13 +608,39 @@ extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, con
     if (special_col >= 0 && special_out) DAE_CUDA(cudaMemsetAsync(special_out, 0, sizeof(float) * M, st));
   }
   GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.k_splits = k_splits; p.atomic = (k_splits > 1 || accumulate) ? 1 : 0; p.alpha = alpha; p.C = C; p.ldc = ldc; p.n_store = n_store;
-  p.special_col = (special_out ? special_col : -1); p.special_out = special_out;
+  p.M = M; p.N = N; p.K = K; p.k_splits = k_splits; p.atomic = (k_splits > 1 || accumulate) ? 1 : 0; p.alpha = alpha;
+  p.C = C; p.ldc = ldc; p.n_store = n_store;
+  p.special_col = (special_out ? special_col : -1); p.special_out = special_out; p.trace = trace;
   Operand A{a_hi, a_lo, lda, a_mn_major}, B{b_hi, b_lo, ldb, b_mn_major};
-  int rc = launch_gemm<256, 2, EPI_STORE, 0, 0>(A, B, p, st);
+  int rc;
+  switch (variant) {
+    case 1: rc = launch_gemm<128, 3, EPI_STORE, 0, 0>(A, B, p, st); break;
+    case 2: rc = launch_gemm<128, 2, EPI_STORE, 0, 0>(A, B, p, st); break;
+    default: rc = launch_gemm<256, 2, EPI_STORE, 0, 0>(A, B, p, st); break;
+  }
   if (rc) return rc;
   DAE_CHECK_LAUNCH("dae_gemm_bf16x3");
   return DAE_OK;
+}
+
+extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
+                               int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
+                               int64_t ldc, int32_t n_store, int32_t special_col, float* special_out, int32_t k_splits,
+                               int32_t accumulate, void* stream) {
+  // 128 x 256 tiles halve the operand traffic per output, but problems with few tiles fill more SMs with 128 x 128 tiles
+  const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256) * (k_splits < 1 ? 1 : k_splits);
+  const int variant = (tiles256 < 120) ? 1 : 0;
+  return gemm_store_dispatch(variant, nullptr, M, N, K, alpha, a_hi, a_lo, lda, a_mn_major, b_hi, b_lo, ldb, b_mn_major, C, ldc,
+                             n_store, special_col, special_out, k_splits, accumulate, stream);
+}
+
+// diagnostic twin of dae_gemm_bf16x3: tile-shape variant + clock64 trace of CTA 0 (trace: int64[1000] device buffer or NULL)
+extern "C" int dae_gemm_bf16x3_tune(int32_t variant, void* trace, int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi,
+                                    const void* a_lo, int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
+                                    int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
+                                    float* special_out, int32_t k_splits, int32_t accumulate, void* stream) {
+  return gemm_store_dispatch(variant, (long long*)trace, M, N, K, alpha, a_hi, a_lo, lda, a_mn_major, b_hi, b_lo, ldb, b_mn_major, C,
+                             ldc, n_store, special_col, special_out, k_splits, accumulate, stream);
 }
 
 extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo, int64_t lde,
@@ -555,7 +656,7 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
   GemmParams p{};
   p.M = Brows; p.N = F; p.K = K; p.k_splits = 1; p.alpha = 1.0f; p.special_col = -1;
   p.indptr = indptr; p.indices = indices; p.values = values; p.rows = rows; p.bv = bv; p.weight = weight; p.stats = stats;
-  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part;
+  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part; p.trace = nullptr;
   Operand A{e_hi, e_lo, lde, 0}, B{w_hi, w_lo, ldw, 0};
   int rc = 0;
 #define DAE_DEC(ACT, LOSS) rc = launch_gemm<256, 2, EPI_DECODE, ACT, LOSS>(A, B, p, st)

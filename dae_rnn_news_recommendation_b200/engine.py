@@ -5,6 +5,8 @@ reference autoencoder/autoencoder.py:233,241) and for `transform` (:494-497).
 PyTorch is plumbing here (device memory, streams, torch.distributed); every arithmetic op of the hot path is a
 kernel from the library.  There is no CPU path.
 """
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -92,7 +94,7 @@ class TrainEngine:
 
     def __init__(self, n_features, n_components, enc_act_func='sigmoid', dec_act_func='sigmoid',
                  loss_func='cross_entropy', opt='gradient_descent', learning_rate=0.1, momentum=0.5, alpha=1.0,
-                 triplet_strategy='batch_all', device='cuda:0', process_group=None):
+                 triplet_strategy='batch_all', device='cuda:0', process_group=None, gemm=None):
         _cabi.lib()  # fail loudly if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _cabi.DaeError('no CUDA device: the DAE hot path has no CPU fallback')
@@ -118,6 +120,11 @@ class TrainEngine:
         self.step_count = 0
         self.stats = torch.zeros(STAT_SLOTS, dtype=torch.float64, device=self.device)
         self._ws_B = 0
+        # dense contractions: 'tc' = tcgen05 bf16x3 kernels (production), 'ffma' = fp32 CUDA-core validation kernels
+        self.gemm_mode = gemm or os.environ.get('DAE_GEMM', 'tc')
+        assert self.gemm_mode in ('tc', 'ffma')
+        self.Hp = (self.H + 1 + 63) // 64 * 64   # K padding of E / W (+1: the all-ones column that turns dW into [dW | dbv])
+        self.Fp = (self.F + 31) // 32 * 32
         self.in_scale = 1.0  # decay noise folds into the encode kernels (utils.decay_noise, autoencoder/utils.py:147-159)
         self.launches = 0  # kernels launched by this engine (bench.py reports it)
         self.timed = None  # {kernel name: [(start_event, end_event), ...]} when per-kernel timing is on
@@ -216,6 +223,20 @@ class TrainEngine:
         if self.strategy in (1, 2):
             self.S = torch.empty(B, B, **f32)
             self.G = torch.empty(B, B, **f32)
+        if self.gemm_mode == 'tc':
+            bf = dict(dtype=torch.bfloat16, device=self.device)
+            self.Bp = (B + 7) // 8 * 8
+            self.E_hi = torch.empty(B, self.Hp, **bf)
+            self.E_lo = torch.empty(B, self.Hp, **bf)
+            self.dZ_hi = torch.empty(B, self.Fp, **bf)
+            self.dZ_lo = torch.empty(B, self.Fp, **bf)
+            self.loss_parts = torch.empty(2 * ((self.F + 255) // 256), B, **f32)
+            if not hasattr(self, 'W_hi'):
+                self.W_hi = torch.empty(self.F, self.Hp, **bf)
+                self.W_lo = torch.empty(self.F, self.Hp, **bf)
+            if self.strategy in (1, 2):
+                self.GG_hi = torch.empty(B, self.Bp, **bf)
+                self.GG_lo = torch.empty(B, self.Bp, **bf)
         self._ws_B = B
 
     # ---- data ----------------------------------------------------------------------------------------------------
@@ -245,6 +266,17 @@ class TrainEngine:
         self._k('dae_sgemm', M, N, K, float(alpha), ptr(A), sam, sak, ptr(Bm), sbn, sbk, float(beta), ptr(Cm), ldc, _stream(),
                 tag=tag)
 
+    # ---- tcgen05 path helpers ----------------------------------------------------------------------------------------------
+    def _tc_gemm(self, M, N, K, alpha, A, a_mn, Bm, b_mn, C, ldc, n_store=0, special_col=-1, special_out=None, k_splits=1,
+                 accumulate=0, tag='gemm'):
+        (a_hi, a_lo), (b_hi, b_lo) = A, Bm
+        self._k('dae_gemm_bf16x3', M, N, K, float(alpha), ptr(a_hi), ptr(a_lo), a_hi.stride(0), a_mn, ptr(b_hi), ptr(b_lo),
+                b_hi.stride(0), b_mn, ptr(C), ldc, n_store, special_col, ptr(special_out), k_splits, accumulate, _stream(),
+                tag=tag)
+
+    def _tc_split(self, src, rows, cols, ld_src, hi, lo, ones_col=-1, scale=1.0):
+        self._k('dae_split_bf16', ptr(src), rows, cols, ld_src, ptr(hi), ptr(lo), hi.stride(0), ones_col, float(scale), _stream())
+
     # ---- one training step -----------------------------------------------------------------------------------------
     def step(self, perm, offset, B, stats_log_row=None, train=True):
         """perm: int32 device tensor (epoch permutation) or None (identity); rows perm[offset:offset+B] form the batch.
@@ -257,8 +289,16 @@ class TrainEngine:
         cc = self.csr_c
         self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
                 self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
+        tc = self.gemm_mode == 'tc'
+        if tc:  # operands of the tensor-core contractions: E (with the all-ones column) and W as bf16 hi/lo pairs
+            self._tc_split(self.E, B, H, H, self.E_hi, self.E_lo, ones_col=H)
+            self._tc_split(self.W, F, H, H, self.W_hi, self.W_lo)
         if strat != 0:
-            self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
+            if tc:
+                Ehl = (self.E_hi, self.E_lo)
+                self._tc_gemm(B, B, H, 1.0, Ehl, 0, Ehl, 0, self.S, B, tag='gemm_gram')
+            else:
+                self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
             if strat == 1:
                 self._k('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
                         ptr(self.stats), st, n_launch=2)
@@ -267,8 +307,13 @@ class TrainEngine:
                         ptr(self.stats), st, n_launch=2)
         self._decode_and_backward(B, self.rows, self.weight if strat != 0 else None, train)
         if strat != 0 and train:  # dE += alpha (G + G^T) E
-            self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
-            self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
+            if tc:
+                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), st)
+                self._tc_gemm(B, H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE, H, accumulate=1,
+                              tag='gemm_dE_tri')
+            else:
+                self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
+                self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
         self._encode_backward_and_update(B, self.rows, self.weight if strat != 0 else None, strat, stats_log_row, train)
 
     def evaluate(self, csr, labels, B=None):
@@ -286,6 +331,8 @@ class TrainEngine:
     def _decode_and_backward(self, B, rows, weight, train=True):
         F, H, st = self.F, self.H, _stream()
         c = self.csr
+        if self.gemm_mode == 'tc':
+            return self._decode_and_backward_tc(B, rows, weight, train)
         self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F, tag='gemm_decode_fwd')  # Z = E.W^T
         self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
                 self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
@@ -294,6 +341,31 @@ class TrainEngine:
         self._k('dae_colsum', ptr(self.Z), B, F, F, ptr(self._gbv()), st)  # dbv
         self._gemm(F, H, B, 1.0, self.Z, 1, F, self.E, 1, H, 0.0, self._gW(), H, tag='gemm_decode_dW')  # dW_dec = dZ^T.E
         self._gemm(B, H, F, 1.0, self.Z, F, 1, self.W, 1, H, 0.0, self.dE, H, tag='gemm_decode_dE')    # dE = dZ.W
+
+    def _decode_and_backward_tc(self, B, rows, weight, train=True):
+        """Decode forward + loss + backward on the tensor cores (bf16x3):  Z = E.W^T with the loss epilogue fused
+        (no Z / D / dense X in HBM), dW = dZ^T.[E | 1] (the extra column is dbv), dE = dZ.W (split-K)."""
+        F, H, st = self.F, self.H, _stream()
+        c = self.csr
+        Ehl, Whl, dZhl = (self.E_hi, self.E_lo), (self.W_hi, self.W_lo), (self.dZ_hi, self.dZ_lo)
+        if self.loss != 2:
+            self._k('dae_decode_fused_bf16x3', B, F, H, ptr(self.E_hi), ptr(self.E_lo), self.Hp, ptr(self.W_hi), ptr(self.W_lo),
+                    self.Hp, ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), ptr(self.bv), self.dec_act, self.loss,
+                    ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.loss_parts), st,
+                    tag='gemm_decode_fwd')
+            self._k('dae_reduce_parts', ptr(self.loss_parts), 2 * ((F + 255) // 256), B, ptr(self.row_loss), st)
+        else:  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
+            self._tc_gemm(B, F, H, 1.0, Ehl, 0, Whl, 0, self.Z, F, tag='gemm_decode_fwd')
+            self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
+                    self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
+            if train:
+                self._tc_split(self.Z, B, F, F, self.dZ_hi, self.dZ_lo)
+        if not train:
+            return
+        # dW_dec (F x H) and dbv (F) in one GEMM: [dW | dbv] = dZ^T . [E | 1]
+        self._tc_gemm(F, H + 1, B, 1.0, dZhl, 1, Ehl, 1, self._gW(), H, n_store=H, special_col=H, special_out=self._gbv(),
+                      tag='gemm_decode_dW')
+        self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=max(1, min(16, F // 512)), tag='gemm_decode_dE')
 
     def _encode_backward_and_update(self, B, rows, weight, strat, stats_log_row, train=True):
         F, H, st = self.F, self.H, _stream()
@@ -326,6 +398,9 @@ class TrainEngine:
         c = self.csr_c
         self._k('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H,
                 self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
+        if self.gemm_mode == 'tc':
+            self._tc_split(self.E, B3, H, H, self.E_hi, self.E_lo, ones_col=H)
+            self._tc_split(self.W, self.F, H, H, self.W_hi, self.W_lo)
         self._decode_and_backward(B3, self.rows, None)
         E, d = self.E, self.dE
         self._k('dae_triplet_explicit', ptr(E[0:B]), ptr(E[B:2 * B]), ptr(E[2 * B:B3]), B, H, H, self.alpha, ptr(d[0:B]),

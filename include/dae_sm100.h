@@ -125,8 +125,9 @@ int dae_sgemm(int32_t M, int32_t N, int32_t K, float alpha, const float* A, int6
  *   k_splits > 1 or accumulate != 0: fp32 atomics into C (C is zeroed first unless accumulate).
  * dae_decode_fused_bf16x3: Z = E.W^T with the decode-loss epilogue fused (D = g(Z+bv), CE/MSE row loss
  *   against the clean CSR rows, dZ written directly as bf16 hi/lo [B x ld_dz]); row_loss_part is
- *   [ceil(F/256) x B] partial row losses (reduce with dae_reduce_parts).  Replaces autoencoder.py:411 +
+ *   [2*ceil(F/256) x B] partial row losses (reduce with dae_reduce_parts).  Replaces autoencoder.py:411 +
  *   triplet_loss_utils.py:262-275 and their autodiff without materialising Z, D or dense X.
+ *   row_loss_part holds 2 * ceil(F/256) partial rows (two column halves per 256-wide tile).
  */
 int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo,
                    int64_t ld_dst, int32_t ones_col, float scale, void* stream);
@@ -136,6 +137,13 @@ int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_
                     int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
                     int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
                     float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
+/* diagnostic twin of dae_gemm_bf16x3: variant 0 = 128x256 tiles / 2 stages, 1 = 128x128 / 3, 2 = 128x128 / 2;
+ * trace = int64[1000] device buffer receiving a clock64 trace of CTA 0 (or NULL) */
+int dae_gemm_bf16x3_tune(int32_t variant, void* trace, int32_t M, int32_t N, int32_t K, float alpha,
+                         const void* a_hi, const void* a_lo, int64_t lda, int32_t a_mn_major,
+                         const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
+                         int64_t ldc, int32_t n_store, int32_t special_col, float* special_out,
+                         int32_t k_splits, int32_t accumulate, void* stream);
 int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
                             int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
                             const int64_t* indptr, const int32_t* indices, const float* values,

@@ -1,0 +1,106 @@
+"""tcgen05 bf16x3 GEMM (dae_gemm_bf16x3 / dae_decode_fused_bf16x3) against fp64 matmul and against the CUDA-core path."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, random_csr, xavier
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _split(x, ld, ones_col=-1):
+    from dae_rnn_news_recommendation_b200 import _cabi
+    rows, cols = x.shape
+    hi = torch.empty(rows, ld, dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty(rows, ld, dtype=torch.bfloat16, device=DEV)
+    _cabi.call('dae_split_bf16', x.data_ptr(), rows, cols, x.stride(0), hi.data_ptr(), lo.data_ptr(), ld, ones_col, 1.0,
+               torch.cuda.current_stream().cuda_stream)
+    return hi, lo
+
+
+def _gemm(M, N, K, A, a_mn, B, b_mn, C, **kw):
+    from dae_rnn_news_recommendation_b200 import _cabi
+    (ah, al), (bh, bl) = A, B
+    _cabi.call('dae_gemm_bf16x3', M, N, K, kw.get('alpha', 1.0), ah.data_ptr(), al.data_ptr(), ah.stride(0), a_mn, bh.data_ptr(),
+               bl.data_ptr(), bh.stride(0), b_mn, C.data_ptr(), C.stride(0), kw.get('n_store', 0), kw.get('special_col', -1),
+               kw['special_out'].data_ptr() if kw.get('special_out') is not None else None, kw.get('k_splits', 1),
+               kw.get('accumulate', 0), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+
+def test_split_is_exact_to_2pow17():
+    x = torch.randn(300, 200, device=DEV) * 3
+    hi, lo = _split(x, 208, ones_col=203)
+    rec = hi[:, :200].float() + lo[:, :200].float()
+    assert float(((rec - x).abs() / x.abs().clamp_min(1e-30)).max()) < 2.0 ** -16
+    assert float(hi[:, 200:203].abs().max()) == 0 and float(hi[:, 203].min()) == 1.0 and float(lo[:, 203].abs().max()) == 0
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (800, 800, 500), (200, 1000, 130), (1000, 501, 800)])
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (1, 1), (0, 1), (1, 0)])
+def test_gemm_all_majorness(M, N, K, a_mn, b_mn):
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    want = (A.double() @ B.double().t()).cpu().numpy()
+    pad = lambda n: (n + 7) // 8 * 8
+    Aop = _split(A.t().contiguous(), pad(M)) if a_mn else _split(A, pad(K))
+    Bop = _split(B.t().contiguous(), pad(N)) if b_mn else _split(B, pad(K))
+    C = torch.full((M, N), float('nan'), device=DEV)
+    _gemm(M, N, K, Aop, a_mn, Bop, b_mn, C)
+    assert rel_err(C.cpu().numpy(), want) < 2e-5
+
+
+def test_gemm_split_k_accumulate_and_special_column():
+    M, N, K = 300, 501, 4000
+    g = torch.Generator(device=DEV).manual_seed(1)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    want = (A.double() @ B.double().t()).cpu().numpy()
+    Aop, Bop = _split(A, K), _split(B, K)
+    C = torch.full((M, 500), float('nan'), device=DEV)
+    sp = torch.full((M,), float('nan'), device=DEV)
+    _gemm(M, N, K, Aop, 0, Bop, 0, C, n_store=500, special_col=500, special_out=sp, k_splits=7, alpha=0.5)
+    assert rel_err(C.cpu().numpy(), 0.5 * want[:, :500]) < 2e-5
+    assert rel_err(sp.cpu().numpy(), 0.5 * want[:, 500]) < 2e-5
+    C2 = torch.ones(M, 500, device=DEV)
+    _gemm(M, 500, K, Aop, 0, Bop, 0, C2, accumulate=1)
+    assert rel_err(C2.cpu().numpy(), 1.0 + want[:, :500]) < 2e-5
+
+
+@pytest.mark.parametrize('loss,dec', [('cross_entropy', 'sigmoid'), ('mean_squared', 'none'), ('mean_squared', 'tanh')])
+def test_fused_decode_matches_unfused(loss, dec):
+    """dae_decode_fused_bf16x3 == dae_sgemm + dae_decode_loss_bwd (the parity-checked CUDA-core path)."""
+    from dae_rnn_news_recommendation_b200 import _cabi
+    from dae_rnn_news_recommendation_b200.engine import DeviceCSR
+    B, F, H = 200, 1000, 52
+    st = torch.cuda.current_stream().cuda_stream
+    x = random_csr(B, F, 30, kind='tfidf' if loss != 'cross_entropy' else 'binary', seed=3)
+    csr = DeviceCSR(x, DEV)
+    E = torch.randn(B, H, device=DEV) * 0.3
+    W = torch.from_numpy(xavier(F, H, 4) * 3).to(DEV)
+    bv = torch.randn(F, device=DEV) * 0.1
+    w = torch.rand(B, device=DEV) * 5
+    stats = torch.zeros(16, dtype=torch.float64, device=DEV)
+    stats[5] = float(w.sum())
+    Z = torch.empty(B, F, device=DEV)
+    _cabi.call('dae_sgemm', B, F, H, 1.0, E.data_ptr(), H, 1, W.data_ptr(), H, 1, 0.0, Z.data_ptr(), F, st)
+    rl = torch.empty(B, device=DEV)
+    _cabi.call('dae_decode_loss_bwd', csr.indptr.data_ptr(), csr.indices.data_ptr(), csr.values.data_ptr(), None, B, F, bv.data_ptr(),
+               _cabi.ACT[dec], _cabi.LOSS[loss], w.data_ptr(), stats.data_ptr(), Z.data_ptr(), F, rl.data_ptr(), st)
+    Hp, Fp = 64, (F + 31) // 32 * 32
+    Ehl, Whl = _split(E, Hp), _split(W, Hp)
+    dzh = torch.full((B, Fp), float('nan'), dtype=torch.bfloat16, device=DEV)
+    dzl = torch.full((B, Fp), float('nan'), dtype=torch.bfloat16, device=DEV)
+    parts = torch.empty(2 * ((F + 255) // 256), B, device=DEV)
+    _cabi.call('dae_decode_fused_bf16x3', B, F, H, Ehl[0].data_ptr(), Ehl[1].data_ptr(), Hp, Whl[0].data_ptr(), Whl[1].data_ptr(), Hp,
+               csr.indptr.data_ptr(), csr.indices.data_ptr(), csr.values.data_ptr(), None, bv.data_ptr(), _cabi.ACT[dec],
+               _cabi.LOSS[loss], w.data_ptr(), stats.data_ptr(), dzh.data_ptr(), dzl.data_ptr(), Fp, parts.data_ptr(), st)
+    rl2 = torch.empty(B, device=DEV)
+    _cabi.call('dae_reduce_parts', parts.data_ptr(), parts.shape[0], B, rl2.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert rel_err(rl2.cpu().numpy(), rl.cpu().numpy()) < 2e-5
+    dz = (dzh.float() + dzl.float())[:, :F]
+    assert rel_err(dz.cpu().numpy(), Z.cpu().numpy()) < 3e-5
+    assert float(dzh[:, F:].float().abs().max()) == 0.0

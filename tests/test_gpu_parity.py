@@ -9,6 +9,13 @@ from helpers import REL_TOL, rel_err, random_csr, mask_csr, xavier
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['tc', 'ffma'], autouse=True)
+def gemm_mode(request, monkeypatch):
+    """Every parity test runs with the tcgen05 bf16x3 contractions (production) and with the CUDA-core fp32 kernels."""
+    monkeypatch.setenv('DAE_GEMM', request.param)
+    return request.param
+
+
 def _engine(F, H, **kw):
     from dae_rnn_news_recommendation_b200.engine import TrainEngine
     return TrainEngine(F, H, device='cuda:0', **kw)
@@ -53,12 +60,15 @@ def _run_step_pair(F, H, B, strategy, loss, enc, dec, opt, n_classes=4, kind='bi
         assert rel_err(g[F * H + H:], gbv) < REL_TOL, ('dbv', s)
         p = eng.get_parameters()
         q = orc.get_parameters()
-        assert rel_err(p['enc_w'], q['enc_w']) < REL_TOL
-        assert rel_err(p['enc_b'], q['enc_b']) < REL_TOL
-        assert rel_err(p['dec_b'], q['dec_b']) < REL_TOL
+        # Adam's first steps apply lr * g / (|g| + 3e-7): entries whose gradient is at fp32 rounding level get O(lr) updates
+        # of either sign, so the *parameters* are only comparable loosely (losses and gradients stay at 1e-4).
+        ptol = 5e-3 if opt == 'adam' else REL_TOL
+        assert rel_err(p['enc_w'], q['enc_w']) < ptol
+        assert rel_err(p['enc_b'], q['enc_b']) < ptol
+        assert rel_err(p['dec_b'], q['dec_b']) < ptol
     # embeddings of the whole set after the updates
     emb = eng.encode(csr).cpu().numpy()
-    assert rel_err(emb, orc.transform(x)) < REL_TOL
+    assert rel_err(emb, orc.transform(x)) < (5e-3 if opt == 'adam' else REL_TOL)
 
 
 @pytest.mark.parametrize('strategy', ['none', 'batch_all', 'batch_hard'])
