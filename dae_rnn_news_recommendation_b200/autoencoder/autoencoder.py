@@ -113,7 +113,10 @@ class DenoisingAutoencoder(object):
             W0 = np.asarray(self.W_init, dtype=np.float32)
             assert W0.shape == (n_features, int(self.n_components))
         else:
-            W0 = utils.xavier_init(n_features, int(self.n_components), self.xavier_init)
+            # own RandomState: the reference draws W0 from TF's graph-level RNG, NOT from the NumPy global stream, so the
+            # global stream (masking noise, shuffles) stays aligned with a seeded reference run
+            rng = np.random.RandomState(self.seed) if self.seed >= 0 else np.random.RandomState()
+            W0 = utils.xavier_init(n_features, int(self.n_components), self.xavier_init, rng=rng)
         eng.set_parameters(W0, np.zeros(int(self.n_components), np.float32), np.zeros(n_features, np.float32))
         if eng.world > 1:
             torch.distributed.broadcast(eng.theta, src=0, group=eng.pg)
@@ -185,15 +188,12 @@ class DenoisingAutoencoder(object):
         bs = utils._resolve_batch_size(n, self.batch_size)
         world = eng.world
         rank = torch.distributed.get_rank(eng.pg) if world > 1 else 0
-        starts = list(range(0, n, bs))
-        if world > 1:  # data parallel: rank r takes batches r, r+P, ... of the shared permutation; full groups only
-            full = [s for s in starts if s + bs <= n]
-            groups = len(full) // world
-            starts = [full[g * world + rank] for g in range(groups)]
+        starts = utils.shard_batch_starts(n, bs, world, rank)  # data parallel: rank r takes batches r, r+P, ...
         log = torch.zeros(max(len(starts), 1), STAT_SLOTS, dtype=torch.float64, device=eng.device)
         if self.rng_mode == 'device' and self.seed >= 0:
             torch.manual_seed(self.seed)
 
+        self.history = []  # additive: per-epoch float64 arrays [steps x STAT_SLOTS] of every step's scalars
         i = -1
         for i in range(self.num_epochs):
             self.train_cost_batch = [], [], []
@@ -208,6 +208,7 @@ class DenoisingAutoencoder(object):
             torch.cuda.synchronize(eng.device)
             self.train_time = time.time() - t0
             vals = log[:len(starts)].cpu().numpy()
+            self.history.append(vals.copy())
             self.train_cost_batch = (list(vals[:, STAT['cost']].astype(np.float32)),
                                      list(vals[:, STAT['ae_loss']].astype(np.float32)) if self.triplet_strategy != 'none' else [],
                                      list(vals[:, STAT['triplet_loss']].astype(np.float32)) if self.triplet_strategy != 'none' else [])

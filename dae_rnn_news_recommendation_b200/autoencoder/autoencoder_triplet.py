@@ -59,12 +59,9 @@ class DenoisingAutoencoderTriplet(DenoisingAutoencoder):
         csr = DeviceCSR(stacked, eng.device)
         eng.set_data(csr, None, None)
         bs = utils._resolve_batch_size(n, self.batch_size)
-        starts = list(range(0, n, bs))
         world = eng.world
-        if world > 1:
-            rank = torch.distributed.get_rank(eng.pg)
-            full = [s for s in starts if s + bs <= n]
-            starts = [full[g * world + rank] for g in range(len(full) // world)]
+        rank = torch.distributed.get_rank(eng.pg) if world > 1 else 0
+        starts = utils.shard_batch_starts(n, bs, world, rank)
         log = torch.zeros(max(len(starts), 1), STAT_SLOTS, dtype=torch.float64, device=eng.device)
         i = -1
         for i in range(self.num_epochs):

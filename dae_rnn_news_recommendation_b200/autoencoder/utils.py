@@ -119,3 +119,18 @@ def get_sparse_ind_val_shape(sparse_m):
     m.sort_indices()
     coo = m.tocoo()
     return np.column_stack((coo.row, coo.col)), coo.data, coo.shape
+
+
+def shard_batch_starts(n_rows, batch_size, world=1, rank=0):
+    """Row offsets (into the epoch's shared permutation) of the batches rank `rank` of `world` trains on.
+
+    world == 1: every batch, the last one short (reference utils.py:53).  world > 1 (data parallel): the permutation
+    is identical on all ranks (same seed), rank r takes batches r, r+P, r+2P, ... and only FULL groups of P full-size
+    batches are used, so every rank runs the same number of steps and the per-step all-reduce always has P contributors.
+    """
+    starts = list(range(0, n_rows, batch_size))
+    if world <= 1:
+        return starts
+    full = [s for s in starts if s + batch_size <= n_rows]
+    groups = len(full) // world
+    return [full[g * world + rank] for g in range(groups)]
