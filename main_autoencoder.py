@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""CLI with the reference's flag surface (reference main_autoencoder.py:23-111) driving the B200 DenoisingAutoencoder.
+
+    python main_autoencoder.py --model_name uci --verbose --encode_full [--data_path datasets/uci_news.snappy.parquet]
+    python main_autoencoder.py --model_name syn --synthetic 100000 --num_epochs 2 --batch_size 800 --verbose
+
+Same flag names, defaults, asserts and `.env` override as the reference (python-dotenv; the two env typos at
+main_autoencoder.py:79-80 are fixed and `adam` is accepted).  Data preparation follows
+main_autoencoder.py:177-238 (CountVectorizer -> binary / tf-idf CSR, factorised labels); the similarity / plotting
+tail (:307-360, matplotlib + sklearn) is outside the accelerated path and is not reproduced.
+"""
+import argparse
+import os
+from pathlib import Path
+
+import numpy as np
+
+_script_path = Path(os.path.dirname(os.path.realpath(__file__)))
+
+
+def _bool_flag(ap, name, default, help_):
+    ap.add_argument('--' + name, dest=name, action='store_true', default=default, help=help_)
+    ap.add_argument('--no' + name, dest=name, action='store_false')
+
+
+def build_parser():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    _bool_flag(ap, 'verbose', False, 'Level of verbosity. 0 - silent, 1 - print log')
+    ap.add_argument('--verbose_step', type=int, default=5)
+    _bool_flag(ap, 'encode_full', False, 'Whether to encode and store the full data set')
+    _bool_flag(ap, 'validation', False, 'Whether to use a validation set and print validation loss')
+    ap.add_argument('--input_format', default='binary', help='["binary", "tfidf"]')
+    ap.add_argument('--label', default='category_publish_name', help='["category_publish_name", "story"]')
+    _bool_flag(ap, 'save_tsv', False, 'Whether to save data in tsv format')
+    ap.add_argument('--train_row', type=int, default=8000)
+    ap.add_argument('--validate_row', type=int, default=2000)
+    _bool_flag(ap, 'restore_previous_data', False, 'restore previous data corresponding to model name')
+    ap.add_argument('--min_df', type=float, default=0)
+    ap.add_argument('--max_df', type=float, default=0.99)
+    ap.add_argument('--max_features', type=int, default=10000)
+    ap.add_argument('--model_name', default='')
+    _bool_flag(ap, 'restore_previous_model', False, 'restore previous model corresponding to model name')
+    ap.add_argument('--seed', type=int, default=-1)
+    ap.add_argument('--compress_factor', type=int, default=20)
+    ap.add_argument('--corr_type', default='masking', help='["none", "masking", "salt_and_pepper", "decay"]')
+    ap.add_argument('--corr_frac', type=float, default=0.3)
+    ap.add_argument('--xavier_init', type=int, default=1)
+    ap.add_argument('--enc_act_func', default='sigmoid')
+    ap.add_argument('--dec_act_func', default='sigmoid')
+    ap.add_argument('--main_dir', default='')
+    ap.add_argument('--loss_func', default='cross_entropy')
+    ap.add_argument('--opt', default='gradient_descent', help='["gradient_descent", "ada_grad", "momentum", "adam"]')
+    ap.add_argument('--learning_rate', type=float, default=0.1)
+    ap.add_argument('--momentum', type=float, default=0.5)
+    ap.add_argument('--num_epochs', type=int, default=50)
+    ap.add_argument('--batch_size', type=float, default=0.1)
+    ap.add_argument('--alpha', type=float, default=1)
+    ap.add_argument('--triplet_strategy', default='batch_all')
+    # additive
+    ap.add_argument('--data_path', default='datasets/uci_news.snappy.parquet')
+    ap.add_argument('--synthetic', type=int, default=0, help='train on N synthetic articles instead of reading --data_path')
+    ap.add_argument('--rng_mode', default='numpy', choices=['numpy', 'device'])
+    return ap
+
+
+def apply_env_overrides(flags):
+    """Same-named environment variables (loaded from .env) override the flags (reference main_autoencoder.py:13-17,36-92)."""
+    dot_env_path = _script_path / '.env'
+    if dot_env_path.exists():
+        try:
+            import dotenv
+            print('.env found, will override all flags using values in .env')
+            dotenv.load_dotenv(dot_env_path)
+        except ImportError:
+            pass
+    for k, v in vars(flags).items():
+        if k in os.environ:
+            raw = os.environ[k]
+            if isinstance(v, bool):
+                setattr(flags, k, True)
+            elif isinstance(v, int):
+                setattr(flags, k, int(raw))
+            elif isinstance(v, float):
+                setattr(flags, k, float(raw))
+            else:
+                setattr(flags, k, raw)
+    return flags
+
+
+def check_flags(F):
+    assert 0. <= F.min_df <= 1.
+    assert 0. <= F.max_df <= 1.
+    assert F.max_features >= 1
+    assert F.enc_act_func in ['sigmoid', 'tanh']
+    assert F.dec_act_func in ['sigmoid', 'tanh', 'none']
+    assert F.corr_type in ['masking', 'salt_and_pepper', 'decay', 'none']
+    assert 0. <= F.corr_frac <= 1.
+    assert F.loss_func in ['cross_entropy', 'mean_squared', 'cosine_proximity']
+    assert F.opt in ['gradient_descent', 'ada_grad', 'momentum', 'adam']
+    assert F.verbose_step > 0
+    assert F.triplet_strategy in ['batch_all', 'batch_hard', 'none']
+    assert F.input_format in ['binary', 'tfidf']
+    assert F.label in ['category_publish_name', 'story']
+    if F.input_format == 'tfidf':
+        assert F.loss_func in ['mean_squared', 'cosine_proximity']
+    if F.main_dir == '':
+        F.main_dir = F.model_name
+    return F
+
+
+def prepare_uci(F):
+    """main_autoencoder.py:177-238 with pandas >= 2 fixes (sort by the article_id column, no DataFrame.append)."""
+    import pandas as pd
+    from sklearn.feature_extraction.text import CountVectorizer, TfidfTransformer
+    df = pd.read_parquet(F.data_path)
+    if 'article_id' in df.columns:
+        df = df.set_index('article_id', drop=False)
+        df.index.name = None
+    df = df.sort_index(ascending=False)
+    df['label_story'] = pd.factorize(df.story)[0]
+    df['label_category_publish_name'] = pd.factorize(df.category_publish_name.apply(lambda s: s.lstrip('即時')))[0]
+    n_tr, n_va = F.train_row, F.validate_row
+    df = df.iloc[0:n_tr + n_va].sample(frac=1)
+    df = df.sort_values('article_id') if 'article_id' in df.columns else df.sort_index()
+    cv = CountVectorizer(stop_words='english', min_df=F.min_df, max_df=F.max_df, max_features=F.max_features, binary=False)
+    X = cv.fit_transform(df.main_content[0:n_tr])
+    Xv = cv.transform(df.main_content[n_tr:n_tr + n_va])
+    tf = TfidfTransformer()
+    Xt, Xtv = tf.fit_transform(X), tf.transform(Xv)
+    X.data = np.ones(len(X.data), dtype=np.float32)
+    Xv.data = np.ones(len(Xv.data), dtype=np.float32)
+    lab = df['label_' + F.label]
+    data = {'binary': (X, Xv), 'tfidf': (Xt, Xtv)}[F.input_format]
+    return data[0].astype(np.float32), data[1].astype(np.float32), lab[0:n_tr].values, lab[n_tr:n_tr + n_va].values
+
+
+def prepare_synthetic(F):
+    from dae_rnn_news_recommendation_b200.synth import make_sparse, make_labels
+    n = F.synthetic
+    X = make_sparse(n, F.max_features, 100, 'binary' if F.input_format == 'binary' else 'tfidf', seed=max(F.seed, 0))
+    lab = make_labels(n, 4, seed=max(F.seed, 0))
+    nv = min(F.validate_row, n // 5)
+    return X[:n - nv], X[n - nv:], lab[:n - nv], lab[n - nv:]
+
+
+def main(argv=None):
+    F = check_flags(apply_env_overrides(build_parser().parse_args(argv)))
+    print(__file__ + ': Start')
+    from dae_rnn_news_recommendation_b200.autoencoder import DenoisingAutoencoder, utils
+    model = DenoisingAutoencoder(
+        seed=F.seed, model_name=F.model_name, compress_factor=F.compress_factor, enc_act_func=F.enc_act_func,
+        dec_act_func=F.dec_act_func, xavier_init=F.xavier_init, corr_type=F.corr_type, corr_frac=F.corr_frac,
+        loss_func=F.loss_func, main_dir=F.main_dir, opt=F.opt, learning_rate=F.learning_rate, momentum=F.momentum,
+        verbose=F.verbose, verbose_step=F.verbose_step, num_epochs=F.num_epochs, batch_size=F.batch_size, alpha=F.alpha,
+        triplet_strategy=F.triplet_strategy, rng_mode=F.rng_mode)
+    trX, vlX, trL, vlL = prepare_synthetic(F) if F.synthetic else prepare_uci(F)
+    print('fit')
+    model.fit(train_set=trX, validation_set=vlX if F.validation else None, train_set_label=trL,
+              validation_set_label=vlL if F.validation else None, restore_previous_model=F.restore_previous_model)
+    with open(model.parameter_file, 'a+') as fh:
+        for k in ('train_row', 'validate_row', 'input_format', 'label', 'restore_previous_data', 'restore_previous_model'):
+            print('{}={}'.format(k, getattr(F, k)), file=fh)
+    print('fit done')
+    # inputs are decayed by (1 - corr_frac) at inference (reference main_autoencoder.py:289-290)
+    enc = model.transform(utils.decay_noise(trX, F.corr_frac), name='article_encoded', save=F.encode_full)
+    enc_v = model.transform(utils.decay_noise(vlX, F.corr_frac), name='article_encoded_validate', save=F.encode_full)
+    print('encoded: train %s validate %s (train_time of the last epoch: %.3f s)' % (enc.shape, enc_v.shape, model.train_time))
+    if F.save_tsv:
+        np.savetxt(model.tsv_dir + 'article_encoded.tsv', enc, delimiter='\t')
+        np.savetxt(model.tsv_dir + 'article_encoded_validate.tsv', enc_v, delimiter='\t')
+    print(__file__ + ': End')
+    return model
+
+
+if __name__ == '__main__':
+    main()
