@@ -192,6 +192,12 @@ class DenoisingAutoencoder(object):
         log = torch.zeros(max(len(starts), 1), STAT_SLOTS, dtype=torch.float64, device=eng.device)
         if self.rng_mode == 'device' and self.seed >= 0:
             torch.manual_seed(self.seed)
+        # Full-size batches are replayed from ONE captured CUDA graph (their offsets are start0 + g * stride, advanced on the
+        # device); a short last batch runs eagerly.  Salt-and-pepper rebuilds the corrupted CSR every epoch -> eager.
+        full = [s0 for s0 in starts if s0 + bs <= n]
+        tail = [s0 for s0 in starts if s0 + bs > n]
+        use_graph = (os.environ.get('DAE_CUDA_GRAPH', '1') == '1' and self.corr_type != 'salt_and_pepper' and len(full) >= 2)
+        perm_buf = torch.zeros(n, dtype=torch.int32, device=eng.device)
 
         self.history = []  # additive: per-epoch float64 arrays [steps x STAT_SLOTS] of every step's scalars
         i = -1
@@ -202,9 +208,18 @@ class DenoisingAutoencoder(object):
             torch.cuda.synchronize(eng.device)
             t0 = time.time()
             self._corrupt_on_device(host_csr, i)
-            perm = self._epoch_permutation(n)
-            for k, s in enumerate(starts):
-                eng.step(perm, s, min(bs, n - s), log[k])
+            perm_buf.copy_(self._epoch_permutation(n))
+            if use_graph:
+                if eng._graph is None:  # first epoch, or the workspaces were re-allocated (e.g. by a larger validation batch)
+                    eng.capture_step_graph(perm_buf, bs, log, row_stride=bs * world)
+                eng.set_step_cursor(full[0], 0)
+                for _ in full:
+                    eng.replay_step()
+                for k, s0 in enumerate(tail):
+                    eng.step(perm_buf, s0, n - s0, log[len(full) + k])
+            else:
+                for k, s0 in enumerate(starts):
+                    eng.step(perm_buf, s0, min(bs, n - s0), log[k])
             torch.cuda.synchronize(eng.device)
             self.train_time = time.time() - t0
             vals = log[:len(starts)].cpu().numpy()

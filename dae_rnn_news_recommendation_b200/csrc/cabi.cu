@@ -30,13 +30,14 @@ namespace dae {
 constexpr int kMaxB = 4096;
 
 __global__ void __launch_bounds__(1024) batch_prepare_kernel(
-    const int32_t* __restrict__ perm, int64_t offset, int B, const float* __restrict__ labels_all, int strategy,
-    int32_t* __restrict__ rows_out, float* __restrict__ labels_out, int32_t* seg_lo,
+    const int32_t* __restrict__ perm, int64_t offset, const int64_t* __restrict__ ctl, int B, const float* __restrict__ labels_all,
+    int strategy, int32_t* __restrict__ rows_out, float* __restrict__ labels_out, int32_t* seg_lo,
     int32_t* seg_hi, float* __restrict__ weight_out, double* __restrict__ stats) {
+  if (ctl) offset += ctl[0];  // device-resident batch cursor (CUDA-graph replay)
   __shared__ float keys[kMaxB];
   __shared__ int vals[kMaxB];
   __shared__ double red[32];
-  int32_t* lo = seg_lo;  // the outputs double as scan scratch (one CTA: __syncthreads orders global writes)
+  int32_t* lo = seg_lo;
   int32_t* hi = seg_hi;
   const int tid = threadIdx.x, nt = blockDim.x;
   int P = 1;
@@ -72,24 +73,17 @@ __global__ void __launch_bounds__(1024) batch_prepare_kernel(
       }
     }
   }
-  // segment starts / ends
+  // class segment of every row: [first index with this label, one past the last) -- binary searches in the sorted keys
   for (int i = tid; i < B; i += nt) {
-    lo[i] = (i == 0 || keys[i] != keys[i - 1]) ? i : 0;
-    hi[i] = (i == B - 1 || keys[i] != keys[i + 1]) ? i + 1 : B;
+    const float k = keys[i];
+    int a = 0, b = i;               // lower bound in [0, i]
+    while (a < b) { const int m = (a + b) >> 1; if (keys[m] < k) a = m + 1; else b = m; }
+    lo[i] = a;
+    a = i + 1; b = B;               // upper bound in (i, B]
+    while (a < b) { const int m = (a + b) >> 1; if (keys[m] <= k) a = m + 1; else b = m; }
+    hi[i] = a;
   }
   __syncthreads();
-  for (int d = 1; d < B; d <<= 1) {  // max-scan from the left, min-scan from the right
-    int nl[(kMaxB + 1023) / 1024], nh[(kMaxB + 1023) / 1024];
-    int c = 0;
-    for (int i = tid; i < B; i += nt, ++c) {
-      nl[c] = (i >= d) ? max(lo[i], lo[i - d]) : lo[i];
-      nh[c] = (i + d < B) ? min(hi[i], hi[i + d]) : hi[i];
-    }
-    __syncthreads();
-    c = 0;
-    for (int i = tid; i < B; i += nt, ++c) { lo[i] = nl[c]; hi[i] = nh[c]; }
-    __syncthreads();
-  }
   double t_part = 0.0, nv_part = 0.0;
   for (int i = tid; i < B; i += nt) {
     const double n = (double)(hi[i] - lo[i]);
@@ -118,9 +112,10 @@ __global__ void __launch_bounds__(1024) batch_prepare_kernel(
 }
 
 // strategy none: keep the permutation order, w = 1, one segment; any B.
-__global__ void batch_rows_kernel(const int32_t* __restrict__ perm, int64_t offset, int B, int32_t* __restrict__ rows_out,
-                                  float* __restrict__ labels_out, int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi,
-                                  float* __restrict__ weight_out, double* __restrict__ stats) {
+__global__ void batch_rows_kernel(const int32_t* __restrict__ perm, int64_t offset, const int64_t* __restrict__ ctl, int B,
+                                  int32_t* __restrict__ rows_out, float* __restrict__ labels_out, int32_t* __restrict__ seg_lo,
+                                  int32_t* __restrict__ seg_hi, float* __restrict__ weight_out, double* __restrict__ stats) {
+  if (ctl) offset += ctl[0];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     rows_out[i] = perm ? perm[offset + i] : (int)(offset + i);
@@ -132,14 +127,27 @@ __global__ void batch_rows_kernel(const int32_t* __restrict__ perm, int64_t offs
   if (i < DAE_STAT_SLOTS) stats[i] = (i == DAE_STAT_SUM_W) ? (double)B : 0.0;
 }
 
+__global__ void step_advance_kernel(int64_t* ctl, int64_t row_stride) {
+  ctl[0] += row_stride;  // batch cursor into the epoch permutation
+  ctl[1] += 1;           // row of the per-epoch stats log
+  ctl[2] += 1;           // optimizer step (Adam bias correction)
+}
+
 }  // namespace dae
 
-extern "C" int dae_batch_prepare(const int32_t* perm, int64_t offset, int32_t B, const float* labels_all,
+extern "C" int dae_step_advance(int64_t* ctl, int64_t row_stride, void* stream) {
+  DAE_REQUIRE(ctl, "dae_step_advance: null ctl");
+  dae::step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctl, row_stride);
+  DAE_CHECK_LAUNCH("dae_step_advance");
+  return DAE_OK;
+}
+
+extern "C" int dae_batch_prepare(const int32_t* perm, int64_t offset, const int64_t* ctl, int32_t B, const float* labels_all,
                                  int32_t strategy, int32_t* rows_out, float* labels_out, int32_t* seg_lo,
                                  int32_t* seg_hi, float* weight_out, double* stats, void* stream) {
   DAE_REQUIRE(B >= 1 && rows_out && stats, "dae_batch_prepare: bad B or null output");
   if (strategy == DAE_TRIPLET_NONE) {
-    dae::batch_rows_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, offset, B, rows_out, labels_out, seg_lo,
+    dae::batch_rows_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, offset, ctl, B, rows_out, labels_out, seg_lo,
                                                                             seg_hi, weight_out, stats);
     DAE_CHECK_LAUNCH("dae_batch_prepare(none)");
     return DAE_OK;
@@ -147,7 +155,7 @@ extern "C" int dae_batch_prepare(const int32_t* perm, int64_t offset, int32_t B,
   DAE_REQUIRE(B <= dae::kMaxB, "dae_batch_prepare: triplet strategies need B <= %d (got %d)", dae::kMaxB, B);
   DAE_REQUIRE(seg_lo && seg_hi, "dae_batch_prepare: null segment outputs");
   DAE_REQUIRE(strategy == DAE_TRIPLET_NONE || labels_all, "dae_batch_prepare: labels required for triplet strategies");
-  dae::batch_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(perm, offset, B, labels_all, strategy, rows_out,
+  dae::batch_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(perm, offset, ctl, B, labels_all, strategy, rows_out,
                                                                  labels_out, seg_lo, seg_hi, weight_out, stats);
   DAE_CHECK_LAUNCH("dae_batch_prepare");
   return DAE_OK;

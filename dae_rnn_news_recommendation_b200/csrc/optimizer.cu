@@ -2,6 +2,7 @@
 //
 // Reference ops replaced: tf.train.{GradientDescent,Adagrad,Momentum,Adam}Optimizer.minimize's apply step
 // (autoencoder/autoencoder.py:451-472, TF-1.12 update rules) and utils.masking_noise (autoencoder/utils.py:94-115).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace dae {
@@ -9,7 +10,13 @@ namespace dae {
 template <int OPT>
 __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ theta, const float* __restrict__ grad,
                                                         float* __restrict__ slot1, float* __restrict__ slot2, int64_t n, float lr,
-                                                        float momentum, float gscale, float lr_t) {
+                                                        float momentum, float gscale, float lr_t, __nv_bfloat16* __restrict__ w_hi,
+                                                        __nv_bfloat16* __restrict__ w_lo, int64_t n_w, int H, int64_t ld_split,
+                                                        const int64_t* __restrict__ ctl) {
+  if (OPT == DAE_OPT_ADAM && ctl) {  // device-resident step counter (CUDA-graph replay): lr_t = lr sqrt(1-b2^t)/(1-b1^t)
+    const double t = (double)ctl[2];
+    lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float g = grad[i] * gscale;
@@ -32,6 +39,13 @@ __global__ void __launch_bounds__(256) optimizer_kernel(float* __restrict__ thet
       p -= lr_t * m / (sqrtf(v) + 1e-8f);
     }
     theta[i] = p;
+    if (w_hi != nullptr && i < n_w) {  // refresh the bf16 hi/lo operand copy of W consumed by the tensor-core GEMMs
+      const int64_t r = i / H;
+      const int64_t o = r * ld_split + (i - r * H);
+      const __nv_bfloat16 h = __float2bfloat16_rn(p);
+      w_hi[o] = h;
+      w_lo[o] = __float2bfloat16_rn(p - __bfloat162float(h));
+    }
   }
 }
 
@@ -73,12 +87,16 @@ __global__ void __launch_bounds__(256) mask_values_kernel(const float* __restric
 }  // namespace dae
 
 extern "C" int dae_optimizer_step(float* theta, const float* grad, float* slot1, float* slot2, int64_t n, int32_t opt, float lr,
-                                  float momentum, float grad_scale, int32_t step, void* stream) {
+                                  float momentum, float grad_scale, int32_t step, const int64_t* ctl, void* w_hi, void* w_lo,
+                                  int32_t F, int32_t H, int64_t ld_split, void* stream) {
   using namespace dae;
   DAE_REQUIRE(theta && grad && n > 0, "dae_optimizer_step: bad arguments");
   DAE_REQUIRE(opt == DAE_OPT_SGD || slot1, "dae_optimizer_step: slot1 required");
   DAE_REQUIRE(opt != DAE_OPT_ADAM || slot2, "dae_optimizer_step: slot2 required for adam");
+  DAE_REQUIRE(!w_hi || (w_lo && F > 0 && H > 0 && ld_split >= H && (int64_t)F * H <= n), "dae_optimizer_step: bad split arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* wh = (__nv_bfloat16*)w_hi; __nv_bfloat16* wl = (__nv_bfloat16*)w_lo;
+  const int64_t n_w = w_hi ? (int64_t)F * H : 0;
   const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
   float lr_t = lr;
   if (opt == DAE_OPT_ADAM) {
@@ -86,10 +104,10 @@ extern "C" int dae_optimizer_step(float* theta, const float* grad, float* slot1,
     lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
   }
   switch (opt) {
-    case DAE_OPT_SGD: optimizer_kernel<DAE_OPT_SGD><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t); break;
-    case DAE_OPT_ADAGRAD: optimizer_kernel<DAE_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t); break;
-    case DAE_OPT_MOMENTUM: optimizer_kernel<DAE_OPT_MOMENTUM><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t); break;
-    case DAE_OPT_ADAM: optimizer_kernel<DAE_OPT_ADAM><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t); break;
+    case DAE_OPT_SGD: optimizer_kernel<DAE_OPT_SGD><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t, wh, wl, n_w, H, ld_split, ctl); break;
+    case DAE_OPT_ADAGRAD: optimizer_kernel<DAE_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t, wh, wl, n_w, H, ld_split, ctl); break;
+    case DAE_OPT_MOMENTUM: optimizer_kernel<DAE_OPT_MOMENTUM><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t, wh, wl, n_w, H, ld_split, ctl); break;
+    case DAE_OPT_ADAM: optimizer_kernel<DAE_OPT_ADAM><<<blocks, 256, 0, st>>>(theta, grad, slot1, slot2, n, lr, momentum, grad_scale, lr_t, wh, wl, n_w, H, ld_split, ctl); break;
     default: set_error("dae_optimizer_step: unknown optimizer %d", opt); return DAE_ERR_BAD_ARG;
   }
   DAE_CHECK_LAUNCH("dae_optimizer_step");

@@ -13,9 +13,9 @@
 
 namespace dae {
 
-constexpr int kTY = 8, kTX = 32, kTJ = 4, kTK = 8;
+constexpr int kTY = 8, kTX = 32, kTJ = 4, kTK = 4;
 constexpr int kJTile = kTY * kTJ;   // 32 positives per j-tile
-constexpr int kKTile = kTX * kTK;   // 256 negatives per k-tile
+constexpr int kKTile = kTX * kTK;   // 128 negatives per k-tile
 constexpr int kTripThreads = kTY * kTX;
 
 __device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -24,8 +24,88 @@ __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ft
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// One 4 x 4 register tile of triplets: sg[a][b] = sigmoid(x_ab) = e/(1+e) with e = exp(x_ab) = u_a v_b (computed as e * 1/(1+e),
+// which keeps full relative accuracy when sigmoid is tiny), lg += sum of log2(1 + e).
+//   TIER 0 (row range < 10): t = 1 + e <= 2.2e4, so products of four t's stay finite: ONE lg2 and ONE rcp per four
+//                            triplets (log of the product; Montgomery batch inversion) -> 0.5 MUFU per triplet.
+//   TIER 1 (row range < 80): one lg2 + one rcp per triplet on the factorised exponentials.
+//   TIER 2                 : direct, overflow-safe evaluation (3 MUFU per triplet).
+template <int TIER>
+__device__ __forceinline__ void triplet_tile(const float (&s_j)[kTJ], const float (&u_j)[kTJ], const float (&s_k)[kTK],
+                                             const float (&v_k)[kTK], float (&sg)[kTJ][kTK], float& lg) {
+#pragma unroll
+  for (int a = 0; a < kTJ; ++a) {
+    if (TIER == 0) {
+      const float e0 = u_j[a] * v_k[0], e1 = u_j[a] * v_k[1], e2 = u_j[a] * v_k[2], e3 = u_j[a] * v_k[3];
+      const float t0 = e0 + 1.0f, t1 = e1 + 1.0f, t2 = e2 + 1.0f, t3 = e3 + 1.0f;
+      const float p01 = t0 * t1, p23 = t2 * t3, P = p01 * p23;
+      lg += fast_lg2(P);
+      const float r = fast_rcp(P);
+      const float r01 = r * p23, r23 = r * p01;
+      sg[a][0] = e0 * (r01 * t1); sg[a][1] = e1 * (r01 * t0); sg[a][2] = e2 * (r23 * t3); sg[a][3] = e3 * (r23 * t2);
+    } else if (TIER == 1) {
+#pragma unroll
+      for (int b = 0; b < kTK; ++b) {
+        const float e = u_j[a] * v_k[b];
+        const float t = e + 1.0f;
+        lg += fast_lg2(t);
+        sg[a][b] = e * fast_rcp(t);
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < kTK; ++b) {
+        const bool valid = (s_j[a] < 1.0e38f) && (s_k[b] > -1.0e38f);
+        const float x = s_k[b] - s_j[a];
+        const float em = fast_ex2(-fabsf(x) * kLog2e);
+        const float t = 1.0f + em;
+        const float r = fast_rcp(t);
+        lg += valid ? (fmaxf(x, 0.0f) * kLog2e + fast_lg2(t)) : 0.0f;
+        sg[a][b] = valid ? (x >= 0.0f ? r : em * r) : 0.0f;
+      }
+    }
+  }
+}
+
 // smem layout (floats): sj[Pj] uj[Pj] gj[Pj] | sk[Pk] vk[Pk] | gk[kTY][Pk]      Pj, Pk = padded counts
-template <bool FAST>
+// sj holds S_ij + 1e-16 so that the reference's positive test (S_ik - S_ij) > 1e-16 is one compare per triplet.
+template <int TIER>
+__device__ __forceinline__ void triplet_sweep(const float* sj, const float* uj, float* gj, const float* sk, const float* vk, float* gk,
+                                              int Pj, int Pk, int Pk_max, int tx, int ty, float& lacc, int& npos) {
+  for (int jt = 0; jt < Pj; jt += kJTile) {
+    float s_j[kTJ], u_j[kTJ], rs[kTJ];
+#pragma unroll
+    for (int a = 0; a < kTJ; ++a) { s_j[a] = sj[jt + ty * kTJ + a]; u_j[a] = uj[jt + ty * kTJ + a]; rs[a] = 0.0f; }
+    for (int kt = 0; kt < Pk; kt += kKTile) {
+      const int q0 = kt + tx * kTK;
+      const float4 s4 = *reinterpret_cast<const float4*>(sk + q0);
+      const float4 v4 = *reinterpret_cast<const float4*>(vk + q0);
+      const float s_k[kTK] = {s4.x, s4.y, s4.z, s4.w};
+      const float v_k[kTK] = {v4.x, v4.y, v4.z, v4.w};
+      float sg[kTJ][kTK];
+      triplet_tile<TIER>(s_j, u_j, s_k, v_k, sg, lacc);
+      float cs[kTK] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int a = 0; a < kTJ; ++a) {
+#pragma unroll
+        for (int b = 0; b < kTK; ++b) {
+          npos += (s_k[b] > s_j[a]) ? 1 : 0;     // (S_ik - S_ij) > 1e-16   (triplet_loss_utils.py:114)
+          rs[a] += sg[a][b];
+          cs[b] += sg[a][b];
+        }
+      }
+      float4* g = reinterpret_cast<float4*>(gk + ty * Pk_max + q0);
+      float4 o = *g;
+      o.x += cs[0]; o.y += cs[1]; o.z += cs[2]; o.w += cs[3];
+      *g = o;
+    }
+#pragma unroll
+    for (int a = 0; a < kTJ; ++a) {
+      const float t = warp_sum(rs[a]);
+      if (tx == 0) gj[jt + ty * kTJ + a] = t;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const float* __restrict__ S, int64_t lds, int B,
                                                                          const int32_t* __restrict__ seg_lo,
                                                                          const int32_t* __restrict__ seg_hi, float* __restrict__ G,
@@ -41,7 +121,11 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
   const float* srow = S + (int64_t)i * lds;
   float* grow = G + (int64_t)i * ldg;
 
-  // row range decides the fast (factorised exp) or the slow (direct, overflow-safe) path
+  if (nj <= 1 || nk == 0) {  // no valid triplet with this anchor
+    for (int c = tid; c < B; c += kTripThreads) grow[c] = 0.0f;
+    return;
+  }
+  // the row's value range picks the evaluation tier
   float mx = -3.0e38f, mn = 3.0e38f;
   for (int c = tid; c < B; c += kTripThreads) { const float s = srow[c]; mx = fmaxf(mx, s); mn = fminf(mn, s); }
 #pragma unroll
@@ -51,8 +135,8 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
   mx = red_f[0]; mn = red_f[8];
 #pragma unroll
   for (int w = 1; w < kTY; ++w) { mx = fmaxf(mx, red_f[w]); mn = fminf(mn, red_f[8 + w]); }
-  const bool fast_ok = (mx - mn) < 80.0f;
-  if (FAST != fast_ok) return;  // the other instantiation's launch handles this row
+  const float range = mx - mn;
+  const int tier = (range < 10.0f) ? 0 : ((range < 80.0f) ? 1 : 2);
   const float mid = 0.5f * (mx + mn);
 
   const int Pj = (nj + kJTile - 1) / kJTile * kJTile;
@@ -64,15 +148,11 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
   float* vk = sk + Pk_max;
   float* gk = vk + Pk_max;  // [kTY][Pk_max]
 
-  if (nj <= 1 || nk == 0) {  // no valid triplet with this anchor
-    for (int c = tid; c < B; c += kTripThreads) grow[c] = 0.0f;
-    return;
-  }
   for (int p = tid; p < Pj; p += kTripThreads) {
     const int c = lo + p;
     const bool ok = (p < nj) && (c != i);
     const float s = ok ? srow[c] : 3.0e38f;               // +huge: never "positive", contributes 0
-    sj[p] = s;
+    sj[p] = ok ? s + 1e-16f : s;   // (S_ik - S_ij) > 1e-16 becomes one compare per triplet
     uj[p] = ok ? fast_ex2((mid - s) * kLog2e) : 0.0f;
     gj[p] = 0.0f;
   }
@@ -86,75 +166,23 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
   for (int e = tid; e < kTY * Pk; e += kTripThreads) gk[(e / Pk) * Pk_max + (e % Pk)] = 0.0f;
   __syncthreads();
 
-  float lacc = 0.0f;
+  float lacc = 0.0f;   // sum of log2(1 + e^x)
   int npos = 0;
-  for (int jt = 0; jt < Pj; jt += kJTile) {
-    float s_j[kTJ], u_j[kTJ], rs[kTJ];
-#pragma unroll
-    for (int a = 0; a < kTJ; ++a) { s_j[a] = sj[jt + ty * kTJ + a]; u_j[a] = uj[jt + ty * kTJ + a]; rs[a] = 0.0f; }
-    for (int kt = 0; kt < Pk; kt += kKTile) {
-      float s_k[kTK], v_k[kTK], cs[kTK];
-      const int q0 = kt + tx * kTK;
-#pragma unroll
-      for (int b = 0; b < kTK; b += 4) {
-        const float4 s4 = *reinterpret_cast<const float4*>(sk + q0 + b);
-        const float4 v4 = *reinterpret_cast<const float4*>(vk + q0 + b);
-        s_k[b] = s4.x; s_k[b + 1] = s4.y; s_k[b + 2] = s4.z; s_k[b + 3] = s4.w;
-        v_k[b] = v4.x; v_k[b + 1] = v4.y; v_k[b + 2] = v4.z; v_k[b + 3] = v4.w;
-      }
-#pragma unroll
-      for (int b = 0; b < kTK; ++b) cs[b] = 0.0f;
-#pragma unroll
-      for (int a = 0; a < kTJ; ++a) {
-#pragma unroll
-        for (int b = 0; b < kTK; ++b) {
-          const float x = s_k[b] - s_j[a];           // triplet_distance (triplet_loss_utils.py:106)
-          npos += (x > 1e-16f) ? 1 : 0;              // :114
-          float sp, sg;
-          if (FAST) {
-            const float t = fmaf(u_j[a], v_k[b], 1.0f);  // 1 + exp(x)
-            sp = fast_lg2(t);                             // log2(1+e^x); scaled by ln2 at the end
-            sg = 1.0f - fast_rcp(t);                      // sigmoid(x)
-          } else {
-            const bool valid = (s_j[a] < 1.0e38f) && (s_k[b] > -1.0e38f);
-            const float ax = fabsf(x);
-            const float em = fast_ex2(-ax * kLog2e);
-            const float t = 1.0f + em;
-            const float r = fast_rcp(t);
-            sp = valid ? (fmaxf(x, 0.0f) * kLog2e + fast_lg2(t)) : 0.0f;
-            sg = valid ? (x >= 0.0f ? r : em * r) : 0.0f;
-          }
-          lacc += sp;
-          rs[a] += sg;
-          cs[b] += sg;
-        }
-      }
-      float* g = gk + ty * Pk_max + q0;
-#pragma unroll
-      for (int b = 0; b < kTK; b += 4) {
-        float4 o = *reinterpret_cast<float4*>(g + b);
-        o.x += cs[b]; o.y += cs[b + 1]; o.z += cs[b + 2]; o.w += cs[b + 3];
-        *reinterpret_cast<float4*>(g + b) = o;
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < kTJ; ++a) {
-      const float t = warp_sum(rs[a]);
-      if (tx == 0) gj[jt + ty * kTJ + a] = t;
-    }
-  }
+  if (tier == 0) triplet_sweep<0>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
+  else if (tier == 1) triplet_sweep<1>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
+  else triplet_sweep<2>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
   __syncthreads();
   const float inv = (float)(1.0 / (stats[DAE_STAT_N_VALID] + 1e-16));
   for (int c = tid; c < B; c += kTripThreads) {
     float g;
     if (c >= lo && c < hi) {
-      g = -gj[c - lo] * inv;
+      g = -gj[c - lo] * inv;      // -sum_k sigma(S_ik - S_ij); the anchor's own slot has u = 0 -> 0
     } else {
       const int q = (c < lo) ? c : c - nj;
       float t = 0.0f;
 #pragma unroll
       for (int w = 0; w < kTY; ++w) t += gk[w * Pk_max + q];
-      g = t * inv;
+      g = t * inv;                // +sum_j sigma(S_ik - S_ij)
     }
     grow[c] = g;
   }
@@ -309,12 +337,10 @@ extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, con
   DAE_REQUIRE(smem + 1024 <= 227 * 1024, "dae_triplet_batch_all: B=%d needs %zu B of shared memory", B, smem);
   static size_t attr_smem = 0;  // opt in to > 48 KB of dynamic shared memory (grown monotonically)
   if (smem > attr_smem) {
-    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  triplet_batch_all_kernel<true><<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
-  triplet_batch_all_kernel<false><<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
+  triplet_batch_all_kernel<<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
   DAE_CHECK_LAUNCH("dae_triplet_batch_all");
   return DAE_OK;
 }

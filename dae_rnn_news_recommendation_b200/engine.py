@@ -120,6 +120,8 @@ class TrainEngine:
         self.step_count = 0
         self.stats = torch.zeros(STAT_SLOTS, dtype=torch.float64, device=self.device)
         self._ws_B = 0
+        self._w_split_valid = False
+        self._graph = None
         # dense contractions: 'tc' = tcgen05 bf16x3 kernels (production), 'ffma' = fp32 CUDA-core validation kernels
         self.gemm_mode = gemm or os.environ.get('DAE_GEMM', 'tc')
         assert self.gemm_mode in ('tc', 'ffma')
@@ -195,6 +197,7 @@ class TrainEngine:
         return self.grad[self.F * self.H + self.H:]
 
     def set_parameters(self, W, bh=None, bv=None):
+        self._w_split_valid = False
         self.W.copy_(torch.as_tensor(np.asarray(W, dtype=np.float32)))
         if bh is not None:
             self.bh.copy_(torch.as_tensor(np.asarray(bh, dtype=np.float32)))
@@ -209,6 +212,7 @@ class TrainEngine:
     def _ensure_ws(self, B):
         if B <= self._ws_B:
             return
+        self._graph = None  # buffers move: a captured step graph (if any) is stale and must be re-captured
         f32 = dict(dtype=torch.float32, device=self.device)
         i32 = dict(dtype=torch.int32, device=self.device)
         self.E = torch.empty(B, self.H, **f32)
@@ -274,17 +278,25 @@ class TrainEngine:
                 b_hi.stride(0), b_mn, ptr(C), ldc, n_store, special_col, ptr(special_out), k_splits, accumulate, _stream(),
                 tag=tag)
 
+    def _ensure_w_split(self):
+        """W as a bf16 hi/lo pair; refreshed by the optimizer kernel after every update, so only (re)built here after
+        parameters were set from outside."""
+        if not self._w_split_valid:
+            self._tc_split(self.W, self.F, self.H, self.H, self.W_hi, self.W_lo)
+            self._w_split_valid = True
+
     def _tc_split(self, src, rows, cols, ld_src, hi, lo, ones_col=-1, scale=1.0):
         self._k('dae_split_bf16', ptr(src), rows, cols, ld_src, ptr(hi), ptr(lo), hi.stride(0), ones_col, float(scale), _stream())
 
     # ---- one training step -----------------------------------------------------------------------------------------
-    def step(self, perm, offset, B, stats_log_row=None, train=True):
+    def step(self, perm, offset, B, stats_log_row=None, train=True, ctl=None):
         """perm: int32 device tensor (epoch permutation) or None (identity); rows perm[offset:offset+B] form the batch.
         stats_log_row: optional float64[STAT_SLOTS] device view receiving this step's scalars."""
         F, H, st = self.F, self.H, _stream()
         self._ensure_ws(B)
         strat = self.strategy
-        self._k('dae_batch_prepare', ptr(perm), int(offset), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
+        self._ctl = ctl  # device int64[4] cursors (offset, log row, optimizer step) when the step is graph-captured
+        self._k('dae_batch_prepare', ptr(perm), int(offset), ptr(ctl), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
                 ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
         cc = self.csr_c
         self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
@@ -292,7 +304,7 @@ class TrainEngine:
         tc = self.gemm_mode == 'tc'
         if tc:  # operands of the tensor-core contractions: E (with the all-ones column) and W as bf16 hi/lo pairs
             self._tc_split(self.E, B, H, H, self.E_hi, self.E_lo, ones_col=H)
-            self._tc_split(self.W, F, H, H, self.W_hi, self.W_lo)
+            self._ensure_w_split()
         if strat != 0:
             if tc:
                 Ehl = (self.E_hi, self.E_lo)
@@ -374,7 +386,7 @@ class TrainEngine:
             self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
                     ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
         self._k('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
-                ptr(stats_log_row), st)
+                ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
         if not train:
             return
         gscale = 1.0
@@ -382,14 +394,18 @@ class TrainEngine:
             torch.distributed.all_reduce(self.grad, group=self.pg)
             gscale = 1.0 / self.world
         self.step_count += 1
+        tc = self.gemm_mode == 'tc'
         self._k('dae_optimizer_step', ptr(self.theta), ptr(self.grad), ptr(self.slot1), ptr(self.slot2), self.n_params,
-                self.opt, self.lr, self.momentum, gscale, self.step_count, st)
+                self.opt, self.lr, self.momentum, gscale, self.step_count, ptr(getattr(self, '_ctl', None)),
+                ptr(self.W_hi) if tc else None,
+                ptr(self.W_lo) if tc else None, F, H, self.Hp, st)
 
     # ---- explicit (anchor, pos, neg) triplets: DenoisingAutoencoderTriplet ---------------------------------------------
     def step_explicit(self, perm, offset, B, n_rows_each, stats_log_row=None):
         """self.csr holds [org; pos; neg] stacked (3*n_rows_each rows). autoencoder_triplet.py:256-258,286-288,303-314."""
         H, st = self.H, _stream()
         B3 = 3 * B
+        self._ctl = None
         self._ensure_ws(B3)
         idx = perm[offset:offset + B] if perm is not None else torch.arange(offset, offset + B, device=self.device, dtype=torch.int32)
         self.rows[:B3] = torch.cat([idx, idx + n_rows_each, idx + 2 * n_rows_each])
@@ -400,7 +416,7 @@ class TrainEngine:
                 self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
         if self.gemm_mode == 'tc':
             self._tc_split(self.E, B3, H, H, self.E_hi, self.E_lo, ones_col=H)
-            self._tc_split(self.W, self.F, H, H, self.W_hi, self.W_lo)
+            self._ensure_w_split()
         self._decode_and_backward(B3, self.rows, None)
         E, d = self.E, self.dE
         self._k('dae_triplet_explicit', ptr(E[0:B]), ptr(E[B:2 * B]), ptr(E[2 * B:B3]), B, H, H, self.alpha, ptr(d[0:B]),
@@ -417,6 +433,58 @@ class TrainEngine:
                 N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, _stream(),
                 tag='encode_transform')
         return out
+
+    # ---- CUDA-graph replay of the step --------------------------------------------------------------------------------
+    def capture_step_graph(self, perm_buf, B, log_buf, row_stride=None):
+        """Capture ONE training step (all kernels, the gradient all-reduce included) into a CUDA graph.  Everything that
+        changes between steps lives in device memory: the batch cursor / log row / optimizer step in `self.ctl`
+        (moved by dae_step_advance, the last node of the graph), the permutation in `perm_buf`, the corrupted values in
+        `self.values_c`.  Returns the graph; replay with `graph.replay()` after `set_step_cursor()`."""
+        if not hasattr(self, 'ctl'):
+            self.ctl = torch.zeros(4, dtype=torch.int64, device=self.device)
+        stride = int(B if row_stride is None else row_stride)
+        saved = (self.step_count, self.timed)
+        self.timed = None
+        # warm-up outside capture (workspace allocation, function attributes, NCCL channels), on a side stream
+        snap = (self.theta.clone(), None if self.slot1 is None else self.slot1.clone(), None if self.slot2 is None else self.slot2.clone(),
+                self.ctl.clone())
+        self.ctl.copy_(torch.tensor([0, 0, 1, 0], dtype=torch.int64))  # warm-up / capture run on the first rows of perm_buf
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+                call('dae_step_advance', ptr(self.ctl), stride, _stream())
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.theta.copy_(snap[0]); self.ctl.copy_(snap[3])
+        if snap[1] is not None: self.slot1.copy_(snap[1])
+        if snap[2] is not None: self.slot2.copy_(snap[2])
+        self._w_split_valid = False
+        self._ensure_ws(B)
+        if self.gemm_mode == 'tc':
+            self._ensure_w_split()
+        torch.cuda.synchronize(self.device)
+        launches0 = self.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+            call('dae_step_advance', ptr(self.ctl), stride, _stream())
+        self.graph_launches = self.launches - launches0 + 1   # kernels per replay
+        self.launches = launches0
+        self.step_count = saved[0]
+        self.timed = saved[1]
+        self._graph = g
+        return g
+
+    def set_step_cursor(self, offset, log_row=0):
+        """Host-side (re)positioning of the device cursors, e.g. at an epoch start."""
+        self.ctl.copy_(torch.tensor([int(offset), int(log_row), self.step_count + 1, 0], dtype=torch.int64), non_blocking=False)
+
+    def replay_step(self):
+        self._graph.replay()
+        self.step_count += 1
+        self.launches += self.graph_launches
 
     def read_stats(self):
         s = self.stats.cpu().numpy()

@@ -77,8 +77,12 @@ int dae_last_error(char* buf, size_t len);
  * and emits for each batch row its dataset row id, label, class segment [seg_lo, seg_hi) and -
  * for batch_all - the closed-form data weight w_i and N_valid.  strategy none: order kept, w = 1.
  * One CTA; B <= 4096.  stats: float64[DAE_STAT_SLOTS], zeroed here, SUM_W / N_VALID filled.
+ * ctl (optional, device int64[4]): per-step cursors kept in device memory so that a captured CUDA graph of the
+ * step can be replayed without host-side argument changes -- ctl[0] is added to `offset`, ctl[1] is the row of the
+ * stats log dae_step_finalize writes, ctl[2] the 1-based optimizer step; dae_step_advance moves all three.
  */
-int dae_batch_prepare(const int32_t* perm, int64_t offset, int32_t B, const float* labels_all,
+int dae_step_advance(int64_t* ctl, int64_t row_stride, void* stream);
+int dae_batch_prepare(const int32_t* perm, int64_t offset, const int64_t* ctl, int32_t B, const float* labels_all,
                       int32_t strategy, int32_t* rows_out, float* labels_out, int32_t* seg_lo,
                       int32_t* seg_hi, float* weight_out, double* stats, void* stream);
 
@@ -189,15 +193,18 @@ int dae_triplet_explicit(const float* E, const float* Ep, const float* En, int32
  * DAE_STAT_SLOTS doubles to stats_log (one row of the per-epoch log) if non-NULL.
  */
 int dae_step_finalize(const float* row_loss, const float* weight, int32_t B, int32_t strategy, float alpha,
-                      double* stats, double* stats_log, void* stream);
+                      double* stats, double* stats_log, const int64_t* ctl, void* stream);
 
 /* ---- K6: optimizer ------------------------------------------------------------------------------------
  * theta <- update(theta, grad * grad_scale) over the flat buffer (autoencoder.py:451-472; TF-1.12 rules:
  * SGD; Adagrad accum(0)=0.1, no eps; Momentum accum=mu*accum+g, theta-=lr*accum; Adam b1 .9 b2 .999 eps 1e-8
  * with lr_t = lr*sqrt(1-b2^t)/(1-b1^t), t = step (1-based)).
+ * If w_hi/w_lo are non-NULL the updated W (first F*H entries) is also written as the bf16 hi/lo pair [F x ld_split]
+ * consumed by the tensor-core GEMMs (fuses dae_split_bf16 of W into the update).
  */
 int dae_optimizer_step(float* theta, const float* grad, float* slot1, float* slot2, int64_t n, int32_t opt,
-                       float lr, float momentum, float grad_scale, int32_t step, void* stream);
+                       float lr, float momentum, float grad_scale, int32_t step, const int64_t* ctl, void* w_hi,
+                       void* w_lo, int32_t F, int32_t H, int64_t ld_split, void* stream);
 
 /* ---- corruption -----------------------------------------------------------------------------------------
  * values_out[p] = keep[p] ? values[p] : 0 where keep is a host-generated byte mask (bit-parity mode with

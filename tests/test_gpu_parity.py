@@ -166,7 +166,7 @@ def test_batch_prepare_permutation_and_weights():
     hi = torch.empty(B, dtype=torch.int32, device=dev)
     w = torch.empty(B, device=dev)
     stats = torch.zeros(16, dtype=torch.float64, device=dev)
-    _cabi.call('dae_batch_prepare', perm.data_ptr(), 300, B, labels.data_ptr(), 1, rows.data_ptr(), lab.data_ptr(),
+    _cabi.call('dae_batch_prepare', perm.data_ptr(), 300, None, B, labels.data_ptr(), 1, rows.data_ptr(), lab.data_ptr(),
                lo.data_ptr(), hi.data_ptr(), w.data_ptr(), stats.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     r = rows.cpu().numpy()
@@ -180,3 +180,37 @@ def test_batch_prepare_permutation_and_weights():
     _, w_ref, _, _ = batch_all_triplet_loss(torch.from_numpy(l), E)
     assert np.allclose(w.cpu().numpy(), w_ref.numpy())
     assert stats.cpu().numpy()[6] == pytest.approx(float(w_ref.sum()) / 3)
+
+
+def test_graph_replay_matches_eager_steps(gemm_mode):
+    """A captured CUDA graph of the step, replayed with device-side cursors, gives the same trajectory as eager launches."""
+    from dae_rnn_news_recommendation_b200.engine import DeviceCSR
+    from dae_rnn_news_recommendation_b200._cabi import STAT
+    F, H, B, steps = 400, 32, 64, 5
+    x = random_csr(B * steps, F, 12, seed=41)
+    xc, _ = mask_csr(x, 0.3, seed=42)
+    labels = np.random.default_rng(43).integers(0, 4, B * steps).astype(np.float32)
+    W0 = xavier(F, H, 44) * 3
+    res = []
+    for mode in ('eager', 'graph'):
+        eng = _engine(F, H, opt='adam', learning_rate=0.01, triplet_strategy='batch_all')
+        eng.set_parameters(W0)
+        eng.set_data(DeviceCSR(x, eng.device), torch.from_numpy(xc.data.astype(np.float32)).to(eng.device),
+                     torch.from_numpy(labels).to(eng.device))
+        perm = torch.from_numpy(np.random.default_rng(45).permutation(B * steps).astype(np.int32)).to(eng.device)
+        log = torch.zeros(steps, 16, dtype=torch.float64, device=eng.device)
+        if mode == 'eager':
+            for s in range(steps):
+                eng.step(perm, s * B, B, log[s])
+        else:
+            eng.capture_step_graph(perm, B, log)
+            eng.set_step_cursor(0, 0)
+            for s in range(steps):
+                eng.replay_step()
+        torch.cuda.synchronize()
+        res.append((log.cpu().numpy().copy(), eng.get_parameters()))
+        assert eng.step_count == steps
+    assert rel_err(res[1][0][:, STAT['cost']], res[0][0][:, STAT['cost']]) < 1e-5
+    assert rel_err(res[1][0][:, STAT['triplet_loss']], res[0][0][:, STAT['triplet_loss']]) < 1e-5
+    assert rel_err(res[1][1]['enc_w'], res[0][1]['enc_w']) < 5e-3  # adam (see _run_step_pair)
+    assert rel_err(res[1][1]['dec_b'], res[0][1]['dec_b']) < 5e-3
