@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--rows', type=int, default=0, help='synthetic articles per rank (default: what the run consumes, <= 100k)')
     ap.add_argument('--flush-l2', action='store_true', help='write a 256 MB buffer between timed steps (per-step events)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying the captured CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=3)
     return ap.parse_args()
 
@@ -218,25 +219,36 @@ def main():
     eng.set_data(csr, None, torch.from_numpy(labels).to(dev))
     steps_per_epoch = n_rows // B
 
+    perm_buf = torch.zeros(n_rows, dtype=torch.int32, device=dev)
+    use_graph = not args.no_graph
+
     def epoch_start(epoch):
         eng.corrupt_masking(w['corr_frac'], seed=1234 + rank, epoch=epoch)           # utils.masking_noise, on device
-        return torch.randperm(n_rows, device=dev, dtype=torch.int32)                  # utils.gen_batches shuffle
+        perm_buf.copy_(torch.randperm(n_rows, device=dev, dtype=torch.int32))         # utils.gen_batches shuffle
 
-    def run(n, first_step, perm_box, log=None, flush=None, evs=None):
+    state = {'epoch': -1}
+
+    def run(n, first_step, log=None, flush=None, evs=None, graph=False):
+        """n steps starting at global step `first_step` (epoch boundaries re-corrupt + re-shuffle inside the window)."""
         for i in range(n):
-            s = first_step + i
-            if s % steps_per_epoch == 0 or perm_box[0] is None:
-                perm_box[0] = epoch_start(s // steps_per_epoch)
+            ep, in_epoch = divmod(first_step + i, steps_per_epoch)
+            if ep != state['epoch']:
+                epoch_start(ep)
+                state['epoch'] = ep
+            if graph and (i == 0 or in_epoch == 0):
+                eng.set_step_cursor(in_epoch * B, i)
             if flush is not None:
                 flush.add_(1.0)
             if evs is not None:
                 evs[i][0].record()
-            eng.step(perm_box[0], (s % steps_per_epoch) * B, B, None if log is None else log[i])
+            if graph:
+                eng.replay_step()
+            else:
+                eng.step(perm_buf, in_epoch * B, B, None if log is None else log[i])
             if evs is not None:
                 evs[i][1].record()
 
-    perm_box = [None]
-    run(W, 0, perm_box)  # warm-up (also allocates the workspaces)
+    run(W, 0)  # warm-up (also allocates the workspaces)
     torch.cuda.synchronize()
 
     # -- per-kernel profile pass (3 steps, every kernel bracketed) to find the dominant kernel
@@ -244,7 +256,7 @@ def main():
             'dae_encode_csr_bwd', 'dae_decode_loss_bwd', 'dae_colsum', 'dae_triplet_batch_all', 'dae_triplet_batch_hard',
             'dae_batch_prepare', 'dae_step_finalize', 'dae_optimizer_step']
     eng.time_kernels(tags)
-    run(3, W, perm_box)
+    run(3, W)
     prof = {k: float(np.sum(v)) / 3.0 for k, v in eng.kernel_times_ms().items() if v}
     eng.time_kernels(None)
     nnz_batch = x.nnz / n_rows * B
@@ -254,9 +266,11 @@ def main():
 
     # -- timed region: EXACTLY K steps, barrier + synchronize on both sides, CUDA events, max over ranks
     log = torch.zeros(K, 16, dtype=torch.float64, device=dev)
+    if use_graph:
+        eng.capture_step_graph(perm_buf, B, log)   # one CUDA graph of the whole step; cursors live in device memory
     flush = torch.zeros(64 * 1024 * 1024, device=dev) if args.flush_l2 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)] if args.flush_l2 else None
-    eng.time_kernels([dominant])
+    eng.time_kernels(None if use_graph else [dominant])
     launches0 = eng.launches
     clocks = Clocks(local)
     if rank == 0:
@@ -268,7 +282,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    run(K, W + 3, perm_box, log=log, flush=flush, evs=evs)
+    run(K, W + 3, log=log, flush=flush, evs=evs, graph=use_graph)
     e1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
@@ -276,6 +290,9 @@ def main():
         dist.barrier()
     ms = e0.elapsed_time(e1) if evs is None else float(sum(a.elapsed_time(b) for a, b in evs))
     gpu_launches = eng.launches - launches0
+    if use_graph:  # events cannot bracket nodes inside a graph: time the dominant kernel in 3 extra eager steps right after
+        eng.time_kernels([dominant])
+        run(3, W + 3 + K)
     dom_ms = eng.kernel_times_ms()[dominant]
     eng.time_kernels(None)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -331,7 +348,7 @@ def main():
         peak_src = 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s'
     roofline = {'kernel': dominant, 'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': unit, 'frac': achieved / peak,
                 'traffic': None, 'peak_source': peak_src, 'avg_launch_ms': dur * 1e3,
-                'share_of_step': float(np.mean(dom_ms)) * len(dom_ms) / K / (ms / K)}
+                'share_of_step': float(np.mean(dom_ms)) / (ms / K), 'launches_per_step': float(gpu_launches) / K}
 
     if rank != 0:
         if world > 1:
@@ -355,7 +372,8 @@ def main():
                    'l2': ('flushed between steps (256 MB write), per-step events' if args.flush_l2 else
                           'inputs larger than L2: every step reads batch rows not touched since the previous epoch; dataset CSR '
                           '+ per-step state (W, Z, grad ~ 92 MB) exceed the 126 MB L2'),
-                   'loss_first_last': [float(losses[0, 0]), float(losses[-1, 0])]},
+                   'loss_first_last': [float(losses[0, 0]), float(losses[-1, 0])],
+                   'launch': 'cuda graph replay' if use_graph else 'eager'},
         'clocks': clk,
         'e2e': {'value': e2e_val, 'unit': 'articles/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 128, 'steps': Ke,
                 'api': 'TrainEngine.run_feed(HostFeed) per step: pinned host batch -> H2D -> step -> D2H scalars, synchronised'},

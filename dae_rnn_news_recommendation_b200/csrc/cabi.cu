@@ -53,7 +53,34 @@ __global__ void __launch_bounds__(1024) batch_prepare_kernel(
     }
   }
   __syncthreads();
-  if (strategy != DAE_TRIPLET_NONE) {
+  if (strategy != DAE_TRIPLET_NONE && P <= 1024) {
+    // bitonic sort with one element per thread held in registers: partner exchange by warp shuffle for strides < 32
+    // (40 of the 55 stages at P = 1024), through shared memory otherwise
+    float key = keys[tid < P ? tid : 0];
+    int val = vals[tid < P ? tid : 0];
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        float okey; int oval;
+        if (j < 32) {
+          okey = __shfl_xor_sync(0xffffffffu, key, j);
+          oval = __shfl_xor_sync(0xffffffffu, val, j);
+        } else {
+          __syncthreads();
+          if (tid < P) { keys[tid] = key; vals[tid] = val; }
+          __syncthreads();
+          okey = keys[(tid ^ j) & (P - 1)];
+          oval = vals[(tid ^ j) & (P - 1)];
+        }
+        const bool up = ((tid & k) == 0), is_lower = ((tid & j) == 0);
+        const bool other_less = (okey < key) || (okey == key && oval < val);
+        const bool take_other = (up == is_lower) ? other_less : !other_less && !(okey == key && oval == val);
+        if (take_other) { key = okey; val = oval; }
+      }
+    }
+    __syncthreads();
+    if (tid < P) { keys[tid] = key; vals[tid] = val; }
+    __syncthreads();
+  } else if (strategy != DAE_TRIPLET_NONE) {
     for (int k = 2; k <= P; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = tid; i < P; i += nt) {

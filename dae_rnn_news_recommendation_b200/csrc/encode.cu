@@ -50,7 +50,7 @@ template <int ACT, int VW, int NC>
 __global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
     const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ W, const float* __restrict__ bh,
-    float* __restrict__ E, int64_t ldE) {
+    float* __restrict__ E, int64_t ldE, int32_t* __restrict__ col_count) {
   __shared__ int s_col[kEncThreads];
   __shared__ float s_val[kEncThreads];
   __shared__ int s_wcnt[kEncThreads / 32];
@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
 
   for (int64_t base = p0; base < p1; base += kEncThreads) {
     const int total = stage_row_chunk(indices, values, base, p1, in_scale, s_col, s_val, s_wcnt);
-#pragma unroll 4
+    if (col_count != nullptr && tid < total) atomicAdd(col_count + s_col[tid], 1);  // per-column entry counts for the backward gather
+#pragma unroll 8
     for (int q = 0; q < total; ++q) {
       const float v = s_val[q];
       const float* wrow = W + (int64_t)s_col[q] * H;
@@ -156,14 +157,156 @@ __global__ void __launch_bounds__(kEncThreads) encode_bwd_kernel(
   }
 }
 
+// ---- backward without fp32 atomics on dW: the batch's stored entries are bucketed by column (counts come from the forward
+// kernel), then every touched row of dW is produced by ONE CTA that gathers v * dA[r,:] over the column's entries.
+__global__ void __launch_bounds__(1024) col_scan_kernel(const int32_t* __restrict__ col_count, int F, int32_t* __restrict__ col_start,
+                                                       int32_t* __restrict__ col_cursor) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (F + 1023) / 1024;
+  const int b = tid * per, e = min(F, b + per);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += col_count[i];
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan of the per-thread sums
+    const int v = (tid >= d) ? s_part[tid - d] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - sum;
+  for (int i = b; i < e; ++i) { col_start[i] = run; col_cursor[i] = run; run += col_count[i]; }
+  if (tid == 1023) col_start[F] = s_part[1023];
+}
+
+// per batch row: dA = dE * f'(A), dbh, and the row's kept entries appended to their column buckets
+template <int ACT>
+__global__ void __launch_bounds__(kEncThreads) encode_bwd_rows_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+    const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ E, const float* __restrict__ bh,
+    float* __restrict__ dE, int64_t ldE, float* __restrict__ dbh, int32_t* __restrict__ col_cursor, int32_t* __restrict__ ent_col,
+    int32_t* __restrict__ ent_row, float* __restrict__ ent_val) {
+  const int tid = threadIdx.x;
+  const int r = blockIdx.x;
+  const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
+  const int64_t p0 = indptr[row], p1 = indptr[row + 1];
+  for (int h = tid; h < H; h += kEncThreads) {
+    const float b = __ldg(bh + h);
+    const float fb = act_fwd<ACT>(b);
+    const float fa = E[(int64_t)r * ldE + h] + fb;
+    const float de = dE[(int64_t)r * ldE + h];
+    const float da = de * act_grad_from_y<ACT>(fa);
+    dE[(int64_t)r * ldE + h] = da;
+    atomicAdd(dbh + h, da - act_grad_from_y<ACT>(fb) * de);
+  }
+  for (int64_t p = p0 + tid; p < p1; p += kEncThreads) {
+    const float v = __ldg(values + p) * in_scale;
+    if (v != 0.0f) {
+      const int col = __ldg(indices + p);
+      const int slot = atomicAdd(col_cursor + col, 1);
+      ent_col[slot] = col;
+      ent_row[slot] = r;
+      ent_val[slot] = v;
+    }
+  }
+}
+
+// Entries are bucketed by column (ent_* sorted by column).  Work is split by ENTRIES, not by columns (word frequencies are
+// Zipfian: a few columns hold hundreds of entries): each CTA takes chunks of kChunk consecutive entries, accumulates
+// v * dA[r,:] in registers while the column stays the same and flushes one vector red.global.add per (chunk, column) run --
+// about (#touched columns + #chunks) vector atomics per step instead of one per entry.
+constexpr int kChunk = 64;
+
+template <int VW, int NC>
+__global__ void __launch_bounds__(kEncThreads) encode_bwd_gather_kernel(const int32_t* __restrict__ col_start, int F,
+                                                                        const int32_t* __restrict__ ent_col,
+                                                                        const int32_t* __restrict__ ent_row,
+                                                                        const float* __restrict__ ent_val, int H,
+                                                                        const float* __restrict__ dA, int64_t ldE,
+                                                                        float* __restrict__ dW) {
+  __shared__ int s_c[kChunk];
+  __shared__ int s_r[kChunk];
+  __shared__ float s_v[kChunk];
+  const int tid = threadIdx.x;
+  const int total = col_start[F];
+  int hcol[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) hcol[c] = (tid + c * kEncThreads) * VW;
+
+  for (int base = blockIdx.x * kChunk; base < total; base += gridDim.x * kChunk) {
+    const int n = min(kChunk, total - base);
+    __syncthreads();
+    if (tid < n) { s_c[tid] = ent_col[base + tid]; s_r[tid] = ent_row[base + tid]; s_v[tid] = ent_val[base + tid]; }
+    __syncthreads();
+    float acc[NC][VW];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int k = 0; k < VW; ++k) acc[c][k] = 0.0f;
+    int cur = s_c[0];
+    for (int q0 = 0; q0 < n; q0 += 8) {
+      float a[8][NC][VW];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {   // eight rows of dA in flight per thread
+        const int q = min(q0 + u, n - 1);
+        const float* arow = dA + (int64_t)s_r[q] * ldE;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (hcol[c] < H) ldg_vec<VW>(arow + hcol[c], a[u][c]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + u;
+        if (q < n) {
+          const int col = s_c[q];
+          if (col != cur) {           // column run ended: flush (uniform branch, every thread sees the same column list)
+            float* wrow = dW + (int64_t)cur * H;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              if (hcol[c] < H) {
+                if constexpr (VW == 4) atomicAdd(reinterpret_cast<float4*>(wrow + hcol[c]), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
+                else if constexpr (VW == 2) atomicAdd(reinterpret_cast<float2*>(wrow + hcol[c]), make_float2(acc[c][0], acc[c][1]));
+                else atomicAdd(wrow + hcol[c], acc[c][0]);
+              }
+#pragma unroll
+              for (int k = 0; k < VW; ++k) acc[c][k] = 0.0f;
+            }
+            cur = col;
+          }
+          const float v = s_v[q];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (hcol[c] < H) {
+#pragma unroll
+              for (int k = 0; k < VW; ++k) acc[c][k] = fmaf(v, a[u][c][k], acc[c][k]);
+            }
+          }
+        }
+      }
+    }
+    float* wrow = dW + (int64_t)cur * H;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (hcol[c] < H) {
+        if constexpr (VW == 4) atomicAdd(reinterpret_cast<float4*>(wrow + hcol[c]), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
+        else if constexpr (VW == 2) atomicAdd(reinterpret_cast<float2*>(wrow + hcol[c]), make_float2(acc[c][0], acc[c][1]));
+        else atomicAdd(wrow + hcol[c], acc[c][0]);
+      }
+    }
+  }
+}
+
 template <int ACT, int VW>
 static int launch_fwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
-                         const int32_t* rows, int H, float in_scale, const float* W, const float* bh, float* E, int64_t ldE) {
+                         const int32_t* rows, int H, float in_scale, const float* W, const float* bh, float* E, int64_t ldE,
+                         int32_t* col_count) {
   switch (nc) {
-    case 1: encode_fwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
-    case 2: encode_fwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
-    case 4: encode_fwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
-    default: encode_fwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE); break;
+    case 1: encode_fwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
+    case 2: encode_fwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
+    case 4: encode_fwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
+    default: encode_fwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
   }
   return 0;
 }
@@ -198,7 +341,7 @@ static inline int pick_nc(int H, int vw) {
 
 extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
                                   int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* W, const float* bh,
-                                  int32_t enc_act, float* E, int64_t ldE, void* stream) {
+                                  int32_t enc_act, float* E, int64_t ldE, int32_t* col_count, void* stream) {
   using namespace dae;
   DAE_REQUIRE(indptr && indices && values && W && bh && E, "dae_encode_csr_fwd: null pointer");
   DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_fwd: bad shape n_rows=%d F=%d H=%d ldE=%lld", n_rows, F, H, (long long)ldE);
@@ -207,11 +350,12 @@ extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices,
   const int nc = pick_nc(H, vw);
   if (nc < 0) { set_error("dae_encode_csr_fwd: H=%d too large for vector width %d", H, vw); return DAE_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (col_count) DAE_CUDA(cudaMemsetAsync(col_count, 0, sizeof(int32_t) * F, st));
   dim3 grid(n_rows);
   DAE_DISPATCH_ACT(enc_act, ACT, {
-    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE);
-    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE);
-    else launch_fwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE);
+    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count);
+    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count);
+    else launch_fwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count);
   });
   DAE_CHECK_LAUNCH("dae_encode_csr_fwd");
   return DAE_OK;
@@ -236,5 +380,36 @@ extern "C" int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices,
     else launch_bwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
   });
   DAE_CHECK_LAUNCH("dae_encode_csr_bwd");
+  return DAE_OK;
+}
+
+extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
+                                         int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* E, const float* bh,
+                                         int32_t enc_act, float* dE, int64_t ldE, float* dW, float* dbh, const int32_t* col_count,
+                                         int32_t* col_start, int32_t* col_cursor, int32_t* ent_col, int32_t* ent_row,
+                                         float* ent_val, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(indptr && indices && values && E && bh && dE && dW && dbh && col_count && col_start && col_cursor && ent_col && ent_row && ent_val,
+              "dae_encode_csr_bwd_gather: null pointer");
+  DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_bwd_gather: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  DAE_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * H, st));
+  if (n_rows == 0) return DAE_OK;
+  int vw = pick_vw(H, ldE, dE);
+  if (pick_vw(H, H, dW) < vw) vw = pick_vw(H, H, dW);
+  const int nc = pick_nc(H, vw);
+  if (nc < 0 || nc > 2) { set_error("dae_encode_csr_bwd_gather: H=%d not supported (use dae_encode_csr_bwd)", H); return DAE_ERR_UNSUPPORTED; }
+  col_scan_kernel<<<1, 1024, 0, st>>>(col_count, F, col_start, col_cursor);
+  DAE_DISPATCH_ACT(enc_act, ACT, {
+    encode_bwd_rows_kernel<ACT><<<n_rows, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dbh, col_cursor,
+                                                               ent_col, ent_row, ent_val);
+  });
+#define DAE_GATHER(VW, NC) encode_bwd_gather_kernel<VW, NC><<<148 * 8, kEncThreads, 0, st>>>(col_start, F, ent_col, ent_row, ent_val, H, dE, ldE, dW)
+#define DAE_GATHER_NC(VW) \
+  do { if (nc == 1) DAE_GATHER(VW, 1); else DAE_GATHER(VW, 2); } while (0)
+  if (vw == 4) DAE_GATHER_NC(4); else if (vw == 2) DAE_GATHER_NC(2); else DAE_GATHER_NC(1);
+#undef DAE_GATHER_NC
+#undef DAE_GATHER
+  DAE_CHECK_LAUNCH("dae_encode_csr_bwd_gather");
   return DAE_OK;
 }

@@ -627,9 +627,12 @@ extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, con
                                int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
                                int64_t ldc, int32_t n_store, int32_t special_col, float* special_out, int32_t k_splits,
                                int32_t accumulate, void* stream) {
-  // 128 x 256 tiles halve the operand traffic per output, but problems with few tiles fill more SMs with 128 x 128 tiles
-  const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256) * (k_splits < 1 ? 1 : k_splits);
-  const int variant = (tiles256 < 120) ? 1 : 0;
+  // 128 x 256 tiles move fewer operand bytes per output, 128 x 128 tiles quantise better onto the 148 SMs: pick the variant
+  // with the smaller (waves x relative tile cost)
+  const int ks = k_splits < 1 ? 1 : k_splits;
+  const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256) * ks, tiles128 = ((M + 127) / 128) * ((N + 127) / 128) * ks;
+  const float cost256 = 2.0f * (float)((tiles256 + 147) / 148), cost128 = 1.1f * (float)((tiles128 + 147) / 148);
+  const int variant = (cost128 < cost256) ? 1 : 0;
   return gemm_store_dispatch(variant, nullptr, M, N, K, alpha, a_hi, a_lo, lda, a_mn_major, b_hi, b_lo, ldb, b_mn_major, C, ldc,
                              n_store, special_col, special_out, k_splits, accumulate, stream);
 }

@@ -114,13 +114,24 @@ __global__ void reduce_parts_kernel(const float* __restrict__ parts, int n_parts
 }
 
 // Single CTA: deterministic reduction of the weighted row losses + the step's scalars.
-__global__ void __launch_bounds__(1024) step_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ weight,
-                                                             int B, int strategy, float alpha, double* __restrict__ stats,
-                                                             double* __restrict__ stats_log, const int64_t* __restrict__ ctl) {
+__global__ void __launch_bounds__(1024) step_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ parts,
+                                                             int n_parts, const float* __restrict__ weight, int B, int strategy,
+                                                             float alpha, double* __restrict__ stats, double* __restrict__ stats_log,
+                                                             const int64_t* __restrict__ ctl) {
   if (stats_log && ctl) stats_log += ctl[1] * DAE_STAT_SLOTS;  // device-resident log cursor (CUDA-graph replay)
   __shared__ double red[32];
   double s = 0.0;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) s += (double)row_loss[i] * (double)(weight ? weight[i] : 1.0f);
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    float l;
+    if (parts) {  // per-tile partial row losses of the fused decode epilogue, summed in a fixed order
+      l = 0.0f;
+#pragma unroll 8
+      for (int q = 0; q < n_parts; ++q) l += parts[(int64_t)q * B + i];
+    } else {
+      l = row_loss[i];
+    }
+    s += (double)l * (double)(weight ? weight[i] : 1.0f);
+  }
   s = block_sum(s, red);
   if (threadIdx.x == 0) {
     const double sum_w = stats[DAE_STAT_SUM_W];
@@ -186,11 +197,11 @@ extern "C" int dae_colsum(const float* M, int32_t n_rows, int32_t n_cols, int64_
   return DAE_OK;
 }
 
-extern "C" int dae_step_finalize(const float* row_loss, const float* weight, int32_t B, int32_t strategy, float alpha,
-                                 double* stats, double* stats_log, const int64_t* ctl, void* stream) {
+extern "C" int dae_step_finalize(const float* row_loss, const float* parts, int32_t n_parts, const float* weight, int32_t B,
+                                 int32_t strategy, float alpha, double* stats, double* stats_log, const int64_t* ctl, void* stream) {
   using namespace dae;
-  DAE_REQUIRE(row_loss && stats && B >= 1, "dae_step_finalize: bad arguments");
-  step_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, weight, B, strategy, alpha, stats, stats_log, ctl);
+  DAE_REQUIRE((row_loss || (parts && n_parts >= 1)) && stats && B >= 1, "dae_step_finalize: bad arguments");
+  step_finalize_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_loss, parts, n_parts, weight, B, strategy, alpha, stats, stats_log, ctl);
   DAE_CHECK_LAUNCH("dae_step_finalize");
   return DAE_OK;
 }

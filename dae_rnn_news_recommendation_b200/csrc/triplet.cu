@@ -88,7 +88,8 @@ __device__ __forceinline__ void triplet_sweep(const float* sj, const float* uj, 
       for (int a = 0; a < kTJ; ++a) {
 #pragma unroll
         for (int b = 0; b < kTK; ++b) {
-          npos += (s_k[b] > s_j[a]) ? 1 : 0;     // (S_ik - S_ij) > 1e-16   (triplet_loss_utils.py:114)
+          // (S_ik - S_ij) > 1e-16 (triplet_loss_utils.py:114): one compare + one predicated add
+          asm("{ .reg .pred p; setp.gt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(npos) : "f"(s_k[b]), "f"(s_j[a]));
           rs[a] += sg[a][b];
           cs[b] += sg[a][b];
         }

@@ -40,6 +40,7 @@ class DeviceCSR:
         m = canonical_csr(m)
         self.shape = m.shape
         self.nnz = int(m.nnz)
+        self.max_row_nnz = int(np.diff(m.indptr).max()) if m.shape[0] else 0
         ip = torch.from_numpy(m.indptr.astype(np.int64))
         ix = torch.from_numpy(m.indices.astype(np.int32))
         va = torch.from_numpy(m.data.astype(np.float32))
@@ -87,6 +88,7 @@ class HostFeed:
 class _CSRView:
     def __init__(self, indptr, indices, values, shape):
         self.indptr, self.indices, self.values, self.shape, self.nnz = indptr, indices, values, shape, values.numel()
+        self.max_row_nnz = None
 
 
 class TrainEngine:
@@ -125,6 +127,11 @@ class TrainEngine:
         # dense contractions: 'tc' = tcgen05 bf16x3 kernels (production), 'ffma' = fp32 CUDA-core validation kernels
         self.gemm_mode = gemm or os.environ.get('DAE_GEMM', 'tc')
         assert self.gemm_mode in ('tc', 'ffma')
+        # encode backward: 'gather' = column-bucketed, atomic-free dW accumulation; 'atomic' = red.global.add per entry
+        self.enc_bwd_mode = os.environ.get('DAE_ENC_BWD', 'gather')
+        if self.H > (1024 if self.H % 4 == 0 else (512 if self.H % 2 == 0 else 256)):
+            self.enc_bwd_mode = 'atomic'
+        self._ent_cap = 0
         self.Hp = (self.H + 1 + 63) // 64 * 64   # K padding of E / W (+1: the all-ones column that turns dW into [dW | dbv])
         self.Fp = (self.F + 31) // 32 * 32
         self.in_scale = 1.0  # decay noise folds into the encode kernels (utils.decay_noise, autoencoder/utils.py:147-159)
@@ -243,6 +250,22 @@ class TrainEngine:
                 self.GG_lo = torch.empty(B, self.Bp, **bf)
         self._ws_B = B
 
+    def _ensure_bucket_scratch(self, B):
+        """Scratch of dae_encode_csr_bwd_gather: per-column counts / offsets and the bucketed (row, value) entries."""
+        c = self.csr_c
+        cap = int(c.nnz) if c.max_row_nnz is None else int(min(c.nnz, B * max(c.max_row_nnz, 1)))
+        if not hasattr(self, 'col_count'):
+            i32 = dict(dtype=torch.int32, device=self.device)
+            self.col_count = torch.zeros(self.F, **i32)
+            self.col_start = torch.zeros(self.F + 1, **i32)
+            self.col_cursor = torch.zeros(self.F, **i32)
+        if cap > self._ent_cap:
+            self._graph = None
+            self.ent_col = torch.empty(cap, dtype=torch.int32, device=self.device)
+            self.ent_row = torch.empty(cap, dtype=torch.int32, device=self.device)
+            self.ent_val = torch.empty(cap, dtype=torch.float32, device=self.device)
+            self._ent_cap = cap
+
     # ---- data ----------------------------------------------------------------------------------------------------
     def set_data(self, csr, values_corrupt=None, labels=None, csr_corrupt=None):
         """csr: DeviceCSR of the CLEAN training rows (loss target); values_corrupt: fp32[nnz] values of the corrupted
@@ -299,8 +322,11 @@ class TrainEngine:
         self._k('dae_batch_prepare', ptr(perm), int(offset), ptr(ctl), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
                 ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
         cc = self.csr_c
+        gather = train and self.enc_bwd_mode == 'gather'
+        if gather:
+            self._ensure_bucket_scratch(B)
         self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
-                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None, st)
         tc = self.gemm_mode == 'tc'
         if tc:  # operands of the tensor-core contractions: E (with the all-ones column) and W as bf16 hi/lo pairs
             self._tc_split(self.E, B, H, H, self.E_hi, self.E_lo, ones_col=H)
@@ -343,6 +369,7 @@ class TrainEngine:
     def _decode_and_backward(self, B, rows, weight, train=True):
         F, H, st = self.F, self.H, _stream()
         c = self.csr
+        self._loss_parts_live = None
         if self.gemm_mode == 'tc':
             return self._decode_and_backward_tc(B, rows, weight, train)
         self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F, tag='gemm_decode_fwd')  # Z = E.W^T
@@ -365,8 +392,9 @@ class TrainEngine:
                     self.Hp, ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), ptr(self.bv), self.dec_act, self.loss,
                     ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.loss_parts), st,
                     tag='gemm_decode_fwd')
-            self._k('dae_reduce_parts', ptr(self.loss_parts), 2 * ((F + 255) // 256), B, ptr(self.row_loss), st)
-        else:  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
+            self._loss_parts_live = self.loss_parts[:2 * ((F + 255) // 256)]
+        else:
+            self._loss_parts_live = None  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
             self._tc_gemm(B, F, H, 1.0, Ehl, 0, Whl, 0, self.Z, F, tag='gemm_decode_fwd')
             self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
                     self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
@@ -377,16 +405,27 @@ class TrainEngine:
         # dW_dec (F x H) and dbv (F) in one GEMM: [dW | dbv] = dZ^T . [E | 1]
         self._tc_gemm(F, H + 1, B, 1.0, dZhl, 1, Ehl, 1, self._gW(), H, n_store=H, special_col=H, special_out=self._gbv(),
                       tag='gemm_decode_dW')
-        self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=max(1, min(16, F // 512)), tag='gemm_decode_dE')
+        self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=self._dE_splits(B), tag='gemm_decode_dE')
+
+    def _dE_splits(self, B):
+        """split-K factor of dE = dZ.W (K = F): enough work items for ~2 waves of the 148 SMs."""
+        tiles = ((B + 127) // 128) * ((self.H + 255) // 256)
+        return int(max(1, min(round(296.0 / tiles), (self.F + 255) // 256)))
 
     def _encode_backward_and_update(self, B, rows, weight, strat, stats_log_row, train=True):
         F, H, st = self.F, self.H, _stream()
         c = self.csr_c
-        if train:
+        if train and self.enc_bwd_mode == 'gather':
+            self._k('dae_encode_csr_bwd_gather', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
+                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), ptr(self.col_count),
+                    ptr(self.col_start), ptr(self.col_cursor), ptr(self.ent_col), ptr(self.ent_row), ptr(self.ent_val), st, n_launch=3,
+                    tag='dae_encode_csr_bwd')
+        elif train:
             self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
                     ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
-        self._k('dae_step_finalize', ptr(self.row_loss), ptr(weight), B, strat, self.alpha, ptr(self.stats),
-                ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
+        parts = getattr(self, '_loss_parts_live', None)   # fused decode epilogue: per-tile partial row losses
+        self._k('dae_step_finalize', ptr(self.row_loss), ptr(parts), 0 if parts is None else parts.shape[0], ptr(weight), B, strat,
+                self.alpha, ptr(self.stats), ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
         if not train:
             return
         gscale = 1.0
@@ -412,8 +451,11 @@ class TrainEngine:
         self.stats.zero_()
         self.stats[STAT['sum_w']] = float(B)  # each of the three reconstruction terms is a mean over B rows
         c = self.csr_c
+        gather = self.enc_bwd_mode == 'gather'
+        if gather:
+            self._ensure_bucket_scratch(B3)
         self._k('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H,
-                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, st)
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None, st)
         if self.gemm_mode == 'tc':
             self._tc_split(self.E, B3, H, H, self.E_hi, self.E_lo, ones_col=H)
             self._ensure_w_split()
@@ -430,7 +472,7 @@ class TrainEngine:
         if out is None:
             out = torch.empty(N, self.H, dtype=torch.float32, device=self.device)
         self._k('dae_encode_csr_fwd', ptr(csr.indptr), ptr(csr.indices), ptr(csr.values if values is None else values), None,
-                N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, _stream(),
+                N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, None, _stream(),
                 tag='encode_transform')
         return out
 

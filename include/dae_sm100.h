@@ -90,11 +90,13 @@ int dae_batch_prepare(const int32_t* perm, int64_t offset, const int64_t* ctl, i
  * E[r,:] = f( in_scale * X[rows[r],:] . W + bh ) - f(bh)      (autoencoder.py:377,389; transform :494-497;
  * in_scale folds utils.decay_noise, utils.py:147-159).  rows == NULL means rows[r] = r.
  * E is written fp32 with leading dimension ldE.  Entries whose value is exactly 0 (masked) are skipped.
+ * col_count (optional, int32[F]): zeroed, then receives the number of kept entries per feature column of the batch --
+ * the bucket sizes dae_encode_csr_bwd_gather needs.
  */
 int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const float* values,
                        const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
                        const float* W, const float* bh, int32_t enc_act, float* E, int64_t ldE,
-                       void* stream);
+                       int32_t* col_count, void* stream);
 
 /* ---- K5: encode backward -------------------------------------------------------------------------
  * dA = dE * f'(A);  dbh = sum_i dA_i - f'(bh) * sum_i dE_i;  dW[c,:] += v * dA[r,:] for every stored
@@ -105,6 +107,18 @@ int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const floa
                        const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
                        const float* E, const float* bh, int32_t enc_act, float* dE, int64_t ldE,
                        float* dW, float* dbh, void* stream);
+
+/* Same result with ~6x fewer atomics on dW: the batch's kept entries are bucketed by feature column (col_count from the
+ * forward call; col_start int32[F+1], col_cursor int32[F], ent_col/ent_row int32[cap], ent_val f32[cap] are
+ * caller-provided scratch, cap >= kept entries of the batch); CTAs then walk fixed-size chunks of the bucketed entry
+ * list, accumulate v * dA[r,:] in registers per column run and issue one vector red.global.add per (chunk, column) run.
+ * Supports H <= 1024 (H % 4 == 0) / 512 (H % 2 == 0) / 256; larger H: use dae_encode_csr_bwd.
+ */
+int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* indices, const float* values,
+                              const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
+                              const float* E, const float* bh, int32_t enc_act, float* dE, int64_t ldE, float* dW,
+                              float* dbh, const int32_t* col_count, int32_t* col_start, int32_t* col_cursor,
+                              int32_t* ent_col, int32_t* ent_row, float* ent_val, void* stream);
 
 /* ---- fp32 reference GEMM (CUDA cores) ----------------------------------------------------------
  * C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + beta * C[m,n]; generic strides.
@@ -188,12 +202,13 @@ int dae_triplet_explicit(const float* E, const float* Ep, const float* En, int32
                          float alpha, float* dE, float* dEp, float* dEn, double* stats, void* stream);
 
 /* ---- step epilogue ---------------------------------------------------------------------------------
- * Reduces row_loss (x weight) deterministically and fills COST / AE_LOSS / TRIPLET_LOSS / FRACTION / NUM
+ * Reduces row_loss -- or, if parts != NULL, the [n_parts x B] per-tile partials of dae_decode_fused_bf16x3 -- (x weight)
+ * deterministically and fills COST / AE_LOSS / TRIPLET_LOSS / FRACTION / NUM
  * of `stats` (autoencoder.py:438,441; triplet_loss_utils.py:127,131,257,259,275); then copies the
  * DAE_STAT_SLOTS doubles to stats_log (one row of the per-epoch log) if non-NULL.
  */
-int dae_step_finalize(const float* row_loss, const float* weight, int32_t B, int32_t strategy, float alpha,
-                      double* stats, double* stats_log, const int64_t* ctl, void* stream);
+int dae_step_finalize(const float* row_loss, const float* parts, int32_t n_parts, const float* weight, int32_t B,
+                      int32_t strategy, float alpha, double* stats, double* stats_log, const int64_t* ctl, void* stream);
 
 /* ---- K6: optimizer ------------------------------------------------------------------------------------
  * theta <- update(theta, grad * grad_scale) over the flat buffer (autoencoder.py:451-472; TF-1.12 rules:
