@@ -161,23 +161,44 @@ __global__ void __launch_bounds__(kEncThreads) encode_bwd_kernel(
 // kernel), then every touched row of dW is produced by ONE CTA that gathers v * dA[r,:] over the column's entries.
 __global__ void __launch_bounds__(1024) col_scan_kernel(const int32_t* __restrict__ col_count, int F, int32_t* __restrict__ col_start,
                                                        int32_t* __restrict__ col_cursor) {
-  __shared__ int s_part[1024];
-  const int tid = threadIdx.x;
-  const int per = (F + 1023) / 1024;
-  const int b = tid * per, e = min(F, b + per);
-  int sum = 0;
-  for (int i = b; i < e; ++i) sum += col_count[i];
-  s_part[tid] = sum;
+  // exclusive scan of the per-column counts: chunks of 8192 staged in shared memory (coalesced in / out), 8 consecutive
+  // elements per thread, warp-shuffle scan of the thread sums, running carry between chunks
+  constexpr int kPer = 8, kChunkElems = 1024 * kPer;
+  __shared__ int s[kChunkElems];
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {  // inclusive scan of the per-thread sums
-    const int v = (tid >= d) ? s_part[tid - d] : 0;
+  for (int base = 0; base < F; base += kChunkElems) {
+    const int n = min(kChunkElems, F - base);
+    for (int i = tid; i < kChunkElems; i += 1024) s[i] = (i < n) ? col_count[base + i] : 0;
     __syncthreads();
-    s_part[tid] += v;
+    int v[kPer], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { v[j] = s[tid * kPer + j]; sum += v[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+      s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    int run = s_carry + s_warp[wid] + incl - sum;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) { s[tid * kPer + j] = run; run += v[j]; }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) { const int x = s[i]; col_start[base + i] = x; col_cursor[base + i] = x; }
+    __syncthreads();
+    if (tid == 1023) s_carry = run;
     __syncthreads();
   }
-  int run = s_part[tid] - sum;
-  for (int i = b; i < e; ++i) { col_start[i] = run; col_cursor[i] = run; run += col_count[i]; }
-  if (tid == 1023) col_start[F] = s_part[1023];
+  if (tid == 0) col_start[F] = s_carry;
 }
 
 // per batch row: dA = dE * f'(A), dbh, and the row's kept entries appended to their column buckets

@@ -137,14 +137,17 @@ struct GemmParams {
   const int64_t* indptr; const int32_t* indices; const float* values; const int32_t* rows;
   const float* bv; const float* weight; const double* stats;
   __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo; int64_t ld_dz;
-  float* row_loss_part;  // [2 * n_tiles_n x M] (two column halves per tile)
+  float* row_loss_part;  // [M] row losses, accumulated with fp32 atomics (zeroed by the launcher)
+  const int32_t* tile_ptr; // [M x (2 * n_tiles_n + 1)]: first CSR entry of every half tile, relative to the row start
   long long* trace;      // optional clock64 trace of CTA 0 (debug)
 };
 
 enum { EPI_STORE = 0, EPI_DECODE = 1 };
 
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
-constexpr int kTcThreadsV2 = 128 + 32 * kEpiWarps; // warps 0-3: TMA / MMA / TMEM-alloc / spare; warps 4-11: epilogue
+// epilogue warps: EW / 4 warps per TMEM lane quarter, each takes 1/(EW/4) of the tile's columns (store epilogue: 8, fused
+// decode epilogue: 8 -- measured: 16 warps do not help, the epilogue is bound by global store requests, not by issue slots)
+constexpr int kEwStore = 8, kEwDecode = 8;
+constexpr int tc_threads(int ew) { return 128 + 32 * ew; }  // warps 0-3: TMA / MMA / TMEM-alloc / spare; then the epilogue warps
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -172,7 +175,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
-__global__ void __launch_bounds__(kTcThreadsV2, 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+__global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore), 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                                                                       const __grid_constant__ CUtensorMap tm_a_lo,
                                                                       const __grid_constant__ CUtensorMap tm_b_hi,
                                                                       const __grid_constant__ CUtensorMap tm_b_lo,
@@ -180,13 +183,16 @@ __global__ void __launch_bounds__(kTcThreadsV2, 1) gemm_bf16x3_kernel(const __gr
   constexpr int A_TILE = BLOCK_M * BLOCK_K * 2;   // bytes of one bf16 A tile (16 KB)
   constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-  constexpr int HALF_N = BLOCK_N / 2;
+  constexpr int kEpiWarps = (EPI == EPI_DECODE) ? kEwDecode : kEwStore;
+  constexpr int kParts = kEpiWarps / 4;          // column parts per tile (one per epilogue warp of a lane quarter)
+  constexpr int HALF_N = BLOCK_N / kParts;       // columns handled by one epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[kAccStages], tmem_empty_bar[kAccStages];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_bias[kAccStages][BLOCK_N];
-  __shared__ __align__(16) float s_tr[kEpiWarps][32][20];  // per-warp transpose staging for coalesced stores (EPI_STORE)
+  __shared__ __align__(16) float s_tr[EPI == EPI_STORE ? kEpiWarps : 1][32][20];  // per-warp transpose staging for coalesced stores
+  __shared__ __align__(16) uint8_t s_stage[EPI == EPI_DECODE ? kEpiWarps : 1][2][32][48];  // bf16 hi / lo dZ blocks [32 rows x 16 cols], rows padded to 48 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(kTcThreadsV2, 1) gemm_bf16x3_kernel(const __gr
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int ew = warp - 4;
     const int quarter = ew & 3;              // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = ew >> 2;                // which half of the tile's columns
+    const int half = ew >> 2;                // which column part of the tile
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     long long* trace = (blockIdx.x == 0 && ew == 0 && lane == 0) ? p.trace : nullptr;
@@ -365,83 +371,119 @@ __global__ void __launch_bounds__(kTcThreadsV2, 1) gemm_bf16x3_kernel(const __gr
         }
       } else {
         // ---- fused decode epilogue: D = g(Z + bv); row loss; dZ -> bf16 hi/lo (autoencoder.py:411, triplet_loss_utils.py:269-275)
+        // 99 % of a bag-of-words target row is zero, so each 16-column chunk is first evaluated branch-free as if x == 0,
+        // stored, and then the row's few stored entries inside the chunk are re-evaluated exactly and patched in place.  The clean CSR row is walked with a cursor (columns are sorted).
+        // The cursor keeps the next THREE entries (c0,v0),(c1,v1),(c2,v2) in registers, loaded well before they are needed, so
+        // the L2 latency of the CSR stream never sits on the column loop.
         int64_t pc = 0, pe = 0;
-        int next_col = 0x7fffffff;
+        int c0 = 0x7fffffff, c1 = 0x7fffffff, c2 = 0x7fffffff;
+        float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
         float sc = 0.0f;
         if (m < p.M) {
           const int64_t row = p.rows ? (int64_t)p.rows[m] : (int64_t)m;
-          pc = p.indptr[row]; pe = p.indptr[row + 1];
-          int64_t lo = pc, hi = pe;   // first stored column >= n0 (columns are sorted inside a row)
-          while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (p.indices[mid] < n0) lo = mid + 1; else hi = mid; }
-          pc = lo;
-          if (pc < pe) next_col = p.indices[pc];
+          const int64_t rbeg = p.indptr[row];
+          const int32_t* tp = p.tile_ptr + (int64_t)m * (kParts * tiles_n + 1) + nb * kParts + half;
+          pc = rbeg + tp[0]; pe = rbeg + tp[1];     // entries of this row that fall into this half tile
+          if (pc < pe) { c0 = p.indices[pc]; v0 = p.values[pc]; }
+          if (pc + 1 < pe) { c1 = p.indices[pc + 1]; v1 = p.values[pc + 1]; }
+          if (pc + 2 < pe) { c2 = p.indices[pc + 2]; v2 = p.values[pc + 2]; }
           sc = (p.weight ? p.weight[m] : 1.0f) / ((float)p.stats[DAE_STAT_SUM_W] + kEps);
         }
+        const bool edge = (n0 + HALF_N > p.N);   // only the last column tile has out-of-range columns
         float lsum = 0.0f;   // CE: accumulated in log2 units, scaled by ln2 at the end
+        // dZ leaves through a per-warp shared-memory transpose: each thread (= batch row) drops the bf16 hi and lo parts of its
+        // 16 values into its two staging rows (patching the row's stored entries there), then the warp writes both 32 x 16
+        // blocks with full 32-byte sectors (16 rows per store instruction).
+        uint8_t* stg_hi = reinterpret_cast<uint8_t*>(&s_stage[ew][0][0][0]);
+        uint8_t* stg_lo = reinterpret_cast<uint8_t*>(&s_stage[ew][1][0][0]);
+        const int rsub = lane >> 1, csub = lane & 1;          // write-out mapping: 16 rows x 2 x 16 B per instruction
+        const int m_base = mb * BLOCK_M + quarter * 32;
+        const int n_lim = edge ? p.N : 0x7fffffff;
 #pragma unroll 1
-        for (int c = 0; c < HALF_N / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
+        for (int c = 0; c < HALF_N / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c * 16, r);
           tmem_ld_wait();
+          const int nc = n0 + c * 16;
           if (m < p.M) {
-            uint32_t hi_pk[16], lo_pk[16];
+            const float* bias = &s_bias[acc][half * HALF_N + c * 16];
+            float zz[16];
+            uint32_t hpk[8], lpk[8];
 #pragma unroll
-            for (int j2 = 0; j2 < 16; ++j2) {
-              float h2[2], l2[2];
+            for (int j2 = 0; j2 < 8; ++j2) {
+              float dzp[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int j = 2 * j2 + e;
-                const int n = n0 + c * 32 + j;
-                const float z = __uint_as_float(r[j]) + s_bias[acc][half * HALF_N + c * 32 + j];
-                const float d = act_fast<ACT>(z);
-                const float gp = act_grad_from_y<ACT>(d);
-                float dz;
+                zz[j] = __uint_as_float(r[j]) + bias[j];
+                const float d = act_fast<ACT>(zz[j]);
+                float dz, lt;
                 if (LOSS == DAE_LOSS_CE) {
                   const float omd = 1.0f - d;
                   const float b = omd + kEps;                 // 1. - decode + 1e-16, left to right (:269)
-                  if (n != next_col) {                        // x == 0 (99 % of the entries)
-                    if (n < p.N) lsum -= f_lg2(b);
-                    // dl * gp = (1/b) * d * omd; omd/b == 1 exactly in fp32 unless omd == 0 (then the product is 0)
-                    dz = (ACT == DAE_ACT_SIGMOID) ? ((omd != 0.0f) ? sc * d : 0.0f) : sc * gp * f_rcp(b);
-                  } else {                                    // densify the clean CSR row on the fly (:264)
-                    const float x = p.values[pc];
-                    ++pc;
-                    next_col = (pc < pe) ? p.indices[pc] : 0x7fffffff;
-                    const float a = d + kEps;
-                    lsum -= x * f_lg2(a) + (1.0f - x) * f_lg2(b);
-                    dz = sc * gp * ((1.0f - x) * f_rcp(b) - x * f_rcp(a));
-                  }
+                  lt = -f_lg2(b);
+                  // dl * g' = d * omd / b; omd / b == 1 exactly in fp32 unless omd == 0 (then the product is 0)
+                  dz = (ACT == DAE_ACT_SIGMOID) ? ((omd != 0.0f) ? sc * d : 0.0f) : sc * act_grad_from_y<ACT>(d) * f_rcp(b);
                 } else {
-                  float x = 0.0f;
-                  if (n == next_col) {
-                    x = p.values[pc];
-                    ++pc;
-                    next_col = (pc < pe) ? p.indices[pc] : 0x7fffffff;
-                  }
-                  const float e2 = x - d;
-                  if (n < p.N) lsum += e2 * e2;
-                  dz = -2.0f * sc * e2 * gp;
+                  lt = d * d;
+                  dz = 2.0f * sc * d * act_grad_from_y<ACT>(d);
                 }
-                if (n >= p.N) dz = 0.0f;
-                h2[e] = __bfloat162float(__float2bfloat16_rn(dz));
-                l2[e] = dz - h2[e];
+                if (edge) { const bool in = (nc + j < n_lim); lt = in ? lt : 0.0f; dz = in ? dz : 0.0f; }  // uniform branch
+                lsum += lt;
+                dzp[e] = dz;
               }
-              hi_pk[j2] = pack_bf16(h2[0], h2[1]);
-              lo_pk[j2] = pack_bf16(l2[0], l2[1]);
+              const uint32_t hp = pack_bf16(dzp[0], dzp[1]);
+              hpk[j2] = hp;
+              lpk[j2] = pack_bf16(dzp[0] - __uint_as_float(hp << 16), dzp[1] - __uint_as_float(hp & 0xffff0000u));
             }
-            const int ncol = n0 + c * 32;
-            if (ncol < p.ld_dz) {  // ld_dz is a multiple of 32 (launcher), so whole 32-column chunks are in range
-              uint4* dh = reinterpret_cast<uint4*>(p.dz_hi + (int64_t)m * p.ld_dz + ncol);
-              uint4* dl4 = reinterpret_cast<uint4*>(p.dz_lo + (int64_t)m * p.ld_dz + ncol);
+            uint4* sh = reinterpret_cast<uint4*>(stg_hi + lane * 48);
+            uint4* sl = reinterpret_cast<uint4*>(stg_lo + lane * 48);
+            sh[0] = make_uint4(hpk[0], hpk[1], hpk[2], hpk[3]); sh[1] = make_uint4(hpk[4], hpk[5], hpk[6], hpk[7]);
+            sl[0] = make_uint4(lpk[0], lpk[1], lpk[2], lpk[3]); sl[1] = make_uint4(lpk[4], lpk[5], lpk[6], lpk[7]);
+            // exact re-evaluation of the stored entries of this row inside the group (densified target, :264)
+            while (c0 < nc + 16) {
+              const float x = v0;
+              const int j = c0 - nc;
+              float zj = zz[0];                               // zz[j] without dynamic register indexing
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                dh[q] = make_uint4(hi_pk[4 * q], hi_pk[4 * q + 1], hi_pk[4 * q + 2], hi_pk[4 * q + 3]);
-                dl4[q] = make_uint4(lo_pk[4 * q], lo_pk[4 * q + 1], lo_pk[4 * q + 2], lo_pk[4 * q + 3]);
+              for (int k = 1; k < 16; ++k) zj = (j == k) ? zz[k] : zj;
+              const float d = act_fast<ACT>(zj);
+              const float gp = act_grad_from_y<ACT>(d);
+              float dz;
+              if (LOSS == DAE_LOSS_CE) {
+                const float a = d + kEps, b = (1.0f - d) + kEps;
+                const float la = f_lg2(a), lb = f_lg2(b);
+                lsum += lb - (x * la + (1.0f - x) * lb);      // replace the x == 0 term by the exact one
+                dz = sc * gp * ((1.0f - x) * f_rcp(b) - x * f_rcp(a));
+              } else {
+                const float e2 = x - d;
+                lsum += e2 * e2 - d * d;
+                dz = -2.0f * sc * e2 * gp;
+              }
+              const __nv_bfloat16 hb = __float2bfloat16_rn(dz);
+              reinterpret_cast<__nv_bfloat16*>(stg_hi + lane * 48)[j] = hb;
+              reinterpret_cast<__nv_bfloat16*>(stg_lo + lane * 48)[j] = __float2bfloat16_rn(dz - __bfloat162float(hb));
+              ++pc;
+              c0 = c1; v0 = v1; c1 = c2; v1 = v2;
+              c2 = 0x7fffffff;
+              if (pc + 2 < pe) { c2 = p.indices[pc + 2]; v2 = p.values[pc + 2]; }
+            }
+          }
+          __syncwarp();
+          if (nc < p.ld_dz) {  // ld_dz is a multiple of 32 (launcher), so whole 16-column groups are in range
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int rr = rsub + 16 * i;
+              if (m_base + rr < p.M) {
+                const int64_t off = (int64_t)(m_base + rr) * p.ld_dz + nc + csub * 8;
+                *reinterpret_cast<uint4*>(p.dz_hi + off) = *reinterpret_cast<const uint4*>(stg_hi + rr * 48 + csub * 16);
+                *reinterpret_cast<uint4*>(p.dz_lo + off) = *reinterpret_cast<const uint4*>(stg_lo + rr * 48 + csub * 16);
               }
             }
           }
+          __syncwarp();
         }
-        if (m < p.M) p.row_loss_part[(int64_t)(nb * 2 + half) * p.M + m] = (LOSS == DAE_LOSS_CE) ? lsum * 0.6931471805599453f : lsum;
+        if (m < p.M) atomicAdd(p.row_loss_part + m, (LOSS == DAE_LOSS_CE) ? lsum * 0.6931471805599453f : lsum);  // 2 * tiles_n partials per row
       }
       tc_fence_before();
       __syncwarp();
@@ -457,6 +499,22 @@ __global__ void __launch_bounds__(kTcThreadsV2, 1) gemm_bf16x3_kernel(const __gr
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
+}
+
+// tile_ptr[m][t] = number of stored entries of batch row m with column < t * half_n (t = 0 .. n_half_tiles): where each
+// half tile of the fused decode epilogue starts in the (sorted) clean CSR row.  One thread per (row, t).
+__global__ void decode_tile_ptr_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                       const int32_t* __restrict__ rows, int M, int n_half_tiles, int half_n,
+                                       int32_t* __restrict__ tile_ptr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (t > n_half_tiles || m >= M) return;
+  const int64_t row = rows ? (int64_t)rows[m] : (int64_t)m;
+  const int64_t b = indptr[row], e = indptr[row + 1];
+  const int target = t * half_n;
+  int64_t lo = b, hi = e;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (indices[mid] < target) lo = mid + 1; else hi = mid; }
+  tile_ptr[(int64_t)m * (n_half_tiles + 1) + t] = (int32_t)(lo - b);
 }
 
 // fp32 -> (bf16 hi, bf16 lo) split, row by row, zero padding up to ld_dst columns; optional 1.0 in column `ones_col`.
@@ -560,13 +618,17 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
   const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.k_splits;
   int sms = 148;
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kTcThreadsV2, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  kern<<<grid, tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore), smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   return DAE_OK;
 }
 
 }  // namespace dae
 
 using namespace dae;
+
+static long long* g_debug_trace = nullptr;
+// diagnostic: the next tcgen05 launches write a clock64 trace of CTA 0 (MMA issuer at [0,500), epilogue warp 0 at [500,1000))
+extern "C" int dae_debug_set_trace(void* trace) { g_debug_trace = (long long*)trace; return DAE_OK; }
 
 extern "C" int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo, int64_t ld_dst,
                               int32_t ones_col, float scale, void* stream) {
@@ -650,8 +712,8 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
                                        const void* w_hi, const void* w_lo, int64_t ldw, const int64_t* indptr, const int32_t* indices,
                                        const float* values, const int32_t* rows, const float* bv, int32_t dec_act, int32_t loss_func,
                                        const float* weight, const double* stats, void* dz_hi, void* dz_lo, int64_t ld_dz,
-                                       float* row_loss_part, void* stream) {
-  DAE_REQUIRE(e_hi && e_lo && w_hi && w_lo && indptr && indices && values && bv && stats && dz_hi && dz_lo && row_loss_part,
+                                       float* row_loss_part, int32_t* tile_ptr, void* stream) {
+  DAE_REQUIRE(e_hi && e_lo && w_hi && w_lo && indptr && indices && values && bv && stats && dz_hi && dz_lo && row_loss_part && tile_ptr,
               "dae_decode_fused_bf16x3: null pointer");
   DAE_REQUIRE(loss_func == DAE_LOSS_CE || loss_func == DAE_LOSS_MSE, "dae_decode_fused_bf16x3: cosine loss uses the unfused path");
   DAE_REQUIRE(lde % 8 == 0 && ldw % 8 == 0 && ld_dz % 32 == 0 && ld_dz >= F, "dae_decode_fused_bf16x3: bad leading dimensions");
@@ -659,7 +721,14 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
   GemmParams p{};
   p.M = Brows; p.N = F; p.K = K; p.k_splits = 1; p.alpha = 1.0f; p.special_col = -1;
   p.indptr = indptr; p.indices = indices; p.values = values; p.rows = rows; p.bv = bv; p.weight = weight; p.stats = stats;
-  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part; p.trace = nullptr;
+  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part; p.trace = g_debug_trace;
+  p.tile_ptr = tile_ptr;
+  DAE_CUDA(cudaMemsetAsync(row_loss_part, 0, sizeof(float) * Brows, st));
+  {
+    const int n_half = (kEwDecode / 4) * ((F + 255) / 256);
+    dim3 grid((n_half + 1 + 127) / 128, Brows);
+    decode_tile_ptr_kernel<<<grid, 128, 0, st>>>(indptr, indices, rows, Brows, n_half, 256 / (kEwDecode / 4), tile_ptr);
+  }
   Operand A{e_hi, e_lo, lde, 0}, B{w_hi, w_lo, ldw, 0};
   int rc = 0;
 #define DAE_DEC(ACT, LOSS) rc = launch_gemm<256, 2, EPI_DECODE, ACT, LOSS>(A, B, p, st)

@@ -51,6 +51,15 @@ __device__ __forceinline__ void triplet_tile(const float (&s_j)[kTJ], const floa
         lg += fast_lg2(t);
         sg[a][b] = e * fast_rcp(t);
       }
+    } else if (TIER == 3) {   // pos_triplets_only (triplet_loss_utils.py:118-120): softplus and COUNTS over positive triplets only
+#pragma unroll
+      for (int b = 0; b < kTK; ++b) {
+        const bool pos = (s_j[a] < 1.0e38f) && (s_k[b] > s_j[a]);   // s_j carries the +1e-16 of the positive test
+        const float x = s_k[b] - s_j[a];
+        const float em = fast_ex2(-fabsf(x) * kLog2e);
+        lg += pos ? (fmaxf(x, 0.0f) * kLog2e + fast_lg2(1.0f + em)) : 0.0f;
+        sg[a][b] = pos ? 1.0f : 0.0f;
+      }
     } else {
 #pragma unroll
       for (int b = 0; b < kTK; ++b) {
@@ -110,7 +119,8 @@ __device__ __forceinline__ void triplet_sweep(const float* sj, const float* uj, 
 __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const float* __restrict__ S, int64_t lds, int B,
                                                                          const int32_t* __restrict__ seg_lo,
                                                                          const int32_t* __restrict__ seg_hi, float* __restrict__ G,
-                                                                         int64_t ldg, double* __restrict__ stats, int Pj_max, int Pk_max) {
+                                                                         int64_t ldg, double* __restrict__ stats, int Pj_max, int Pk_max,
+                                                                         int pos_only) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_f[32];
   __shared__ double red_d[32];
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
 #pragma unroll
   for (int w = 1; w < kTY; ++w) { mx = fmaxf(mx, red_f[w]); mn = fminf(mn, red_f[8 + w]); }
   const float range = mx - mn;
-  const int tier = (range < 10.0f) ? 0 : ((range < 80.0f) ? 1 : 2);
+  const int tier = pos_only ? 3 : ((range < 10.0f) ? 0 : ((range < 80.0f) ? 1 : 2));
   const float mid = 0.5f * (mx + mn);
 
   const int Pj = (nj + kJTile - 1) / kJTile * kJTile;
@@ -171,9 +181,10 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
   int npos = 0;
   if (tier == 0) triplet_sweep<0>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
   else if (tier == 1) triplet_sweep<1>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
-  else triplet_sweep<2>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
+  else if (tier == 2) triplet_sweep<2>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
+  else triplet_sweep<3>(sj, uj, gj, sk, vk, gk, Pj, Pk, Pk_max, tx, ty, lacc, npos);
   __syncthreads();
-  const float inv = (float)(1.0 / (stats[DAE_STAT_N_VALID] + 1e-16));
+  const float inv = pos_only ? 1.0f : (float)(1.0 / (stats[DAE_STAT_N_VALID] + 1e-16));  // pos_only: G holds raw counts
   for (int c = tid; c < B; c += kTripThreads) {
     float g;
     if (c >= lo && c < hi) {
@@ -328,7 +339,7 @@ __global__ void triplet_explicit_kernel(const float* __restrict__ E, const float
 }  // namespace dae
 
 extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, const int32_t* seg_lo, const int32_t* seg_hi, float* G,
-                                     int64_t ldg, double* stats, void* stream) {
+                                     int64_t ldg, double* stats, int32_t pos_only, void* stream) {
   using namespace dae;
   DAE_REQUIRE(S && seg_lo && seg_hi && G && stats && B >= 1 && B <= 4096 && lds >= B && ldg >= B, "dae_triplet_batch_all: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -341,7 +352,7 @@ extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, con
     DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  triplet_batch_all_kernel<<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk);
+  triplet_batch_all_kernel<<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk, pos_only);
   DAE_CHECK_LAUNCH("dae_triplet_batch_all");
   return DAE_OK;
 }

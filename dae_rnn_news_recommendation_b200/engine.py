@@ -242,6 +242,7 @@ class TrainEngine:
             self.dZ_hi = torch.empty(B, self.Fp, **bf)
             self.dZ_lo = torch.empty(B, self.Fp, **bf)
             self.loss_parts = torch.empty(2 * ((self.F + 255) // 256), B, **f32)
+            self.tile_ptr = torch.empty(B, 4 * ((self.F + 255) // 256) + 1, **i32)
             if not hasattr(self, 'W_hi'):
                 self.W_hi = torch.empty(self.F, self.Hp, **bf)
                 self.W_lo = torch.empty(self.F, self.Hp, **bf)
@@ -339,7 +340,7 @@ class TrainEngine:
                 self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
             if strat == 1:
                 self._k('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
-                        ptr(self.stats), st, n_launch=2)
+                        ptr(self.stats), 0, st)
             else:
                 self._k('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
                         ptr(self.stats), st, n_launch=2)
@@ -390,9 +391,9 @@ class TrainEngine:
         if self.loss != 2:
             self._k('dae_decode_fused_bf16x3', B, F, H, ptr(self.E_hi), ptr(self.E_lo), self.Hp, ptr(self.W_hi), ptr(self.W_lo),
                     self.Hp, ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), ptr(self.bv), self.dec_act, self.loss,
-                    ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.loss_parts), st,
-                    tag='gemm_decode_fwd')
-            self._loss_parts_live = self.loss_parts[:2 * ((F + 255) // 256)]
+                    ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.row_loss), ptr(self.tile_ptr), st,
+                    n_launch=2, tag='gemm_decode_fwd')
+            self._loss_parts_live = None
         else:
             self._loss_parts_live = None  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
             self._tc_gemm(B, F, H, 1.0, Ehl, 0, Whl, 0, self.Z, F, tag='gemm_decode_fwd')

@@ -142,10 +142,10 @@ int dae_sgemm(int32_t M, int32_t N, int32_t K, float alpha, const float* A, int6
  *   columns n < n_store go to C; column special_col (if special_out != NULL) goes to special_out[m].
  *   k_splits > 1 or accumulate != 0: fp32 atomics into C (C is zeroed first unless accumulate).
  * dae_decode_fused_bf16x3: Z = E.W^T with the decode-loss epilogue fused (D = g(Z+bv), CE/MSE row loss
- *   against the clean CSR rows, dZ written directly as bf16 hi/lo [B x ld_dz]); row_loss_part is
- *   [2*ceil(F/256) x B] partial row losses (reduce with dae_reduce_parts).  Replaces autoencoder.py:411 +
+ *   against the clean CSR rows, dZ written directly as bf16 hi/lo [B x ld_dz]); row_loss_part is the
+ *   [B] row-loss vector (zeroed here, accumulated with fp32 atomics, one add per half tile).  Replaces autoencoder.py:411 +
  *   triplet_loss_utils.py:262-275 and their autodiff without materialising Z, D or dense X.
- *   row_loss_part holds 2 * ceil(F/256) partial rows (two column halves per 256-wide tile).
+  *   tile_ptr is int32 scratch [Brows x (2*ceil(F/256) + 1)] (per-row CSR offsets of every 128-column part, filled here).
  */
 int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo,
                    int64_t ld_dst, int32_t ones_col, float scale, void* stream);
@@ -162,12 +162,14 @@ int dae_gemm_bf16x3_tune(int32_t variant, void* trace, int32_t M, int32_t N, int
                          const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
                          int64_t ldc, int32_t n_store, int32_t special_col, float* special_out,
                          int32_t k_splits, int32_t accumulate, void* stream);
+/* diagnostic: subsequent fused-decode launches write a clock64 trace of CTA 0 into trace (int64[1000] device buffer; NULL = off) */
+int dae_debug_set_trace(void* trace);
 int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
                             int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
                             const int64_t* indptr, const int32_t* indices, const float* values,
                             const int32_t* rows, const float* bv, int32_t dec_act, int32_t loss_func,
                             const float* weight, const double* stats, void* dz_hi, void* dz_lo,
-                            int64_t ld_dz, float* row_loss_part, void* stream);
+                            int64_t ld_dz, float* row_loss_part, int32_t* tile_ptr, void* stream);
 /* out[i] = sum_p parts[p * n + i] (deterministic reduction of the per-tile row-loss partials) */
 int dae_reduce_parts(const float* parts, int32_t n_parts, int32_t n, float* out, void* stream);
 
@@ -190,10 +192,12 @@ int dae_colsum(const float* M, int32_t n_rows, int32_t n_cols, int64_t ld, float
  * batch_all (triplet_loss_utils.py:79-131, pos_triplets_only=False as called at autoencoder.py:430):
  *   rows must be label sorted (dae_batch_prepare). S = E.E^T is an input (B x B, ld lds).
  *   Writes G (B x B): dL_tri/dS, accumulates loss sum / positive count into stats.
+ *   pos_only != 0 (pos_triplets_only=True, :118-120; never used by the model): the loss sum covers positive triplets
+ *   only and G receives raw COUNTS of positive triplets (G[i,j] = -#k, G[i,k] = +#j) from which the caller derives the weights.
  * batch_hard (triplet_loss_utils.py:202-259): also writes the data weight (w) and sum_w.
  */
 int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, const int32_t* seg_lo, const int32_t* seg_hi,
-                          float* G, int64_t ldg, double* stats, void* stream);
+                          float* G, int64_t ldg, double* stats, int32_t pos_only, void* stream);
 int dae_triplet_batch_hard(const float* S, int64_t lds, int32_t B, const float* labels, float* G, int64_t ldg,
                            float* weight, double* stats, void* stream);
 /* explicit triplets (autoencoder_triplet.py:308-311): loss = mean softplus(e.en - e.ep); ACCUMULATES alpha * dloss

@@ -94,11 +94,11 @@ def test_fused_decode_matches_unfused(loss, dec):
     dzh = torch.full((B, Fp), float('nan'), dtype=torch.bfloat16, device=DEV)
     dzl = torch.full((B, Fp), float('nan'), dtype=torch.bfloat16, device=DEV)
     parts = torch.empty(2 * ((F + 255) // 256), B, device=DEV)
+    tptr = torch.empty(B, 4 * ((F + 255) // 256) + 1, dtype=torch.int32, device=DEV)
     _cabi.call('dae_decode_fused_bf16x3', B, F, H, Ehl[0].data_ptr(), Ehl[1].data_ptr(), Hp, Whl[0].data_ptr(), Whl[1].data_ptr(), Hp,
                csr.indptr.data_ptr(), csr.indices.data_ptr(), csr.values.data_ptr(), None, bv.data_ptr(), _cabi.ACT[dec],
-               _cabi.LOSS[loss], w.data_ptr(), stats.data_ptr(), dzh.data_ptr(), dzl.data_ptr(), Fp, parts.data_ptr(), st)
-    rl2 = torch.empty(B, device=DEV)
-    _cabi.call('dae_reduce_parts', parts.data_ptr(), parts.shape[0], B, rl2.data_ptr(), st)
+               _cabi.LOSS[loss], w.data_ptr(), stats.data_ptr(), dzh.data_ptr(), dzl.data_ptr(), Fp, parts.data_ptr(), tptr.data_ptr(), st)
+    rl2 = parts.view(-1)[:B]
     torch.cuda.synchronize()
     assert rel_err(rl2.cpu().numpy(), rl.cpu().numpy()) < 2e-5
     dz = (dzh.float() + dzl.float())[:, :F]
