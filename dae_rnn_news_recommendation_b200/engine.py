@@ -427,18 +427,23 @@ class TrainEngine:
         parts = getattr(self, '_loss_parts_live', None)   # fused decode epilogue: per-tile partial row losses
         self._k('dae_step_finalize', ptr(self.row_loss), ptr(parts), 0 if parts is None else parts.shape[0], ptr(weight), B, strat,
                 self.alpha, ptr(self.stats), ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
-        if not train:
+        if not train or getattr(self, '_defer_update', False):
             return
+        self._apply_update()
+
+    def _apply_update(self, reduce=True):
+        """Data parallel: ONE all-reduce of the flat [dW | dbh | dbv] buffer, then the fused optimizer (1/P folded in)."""
+        F, H, st = self.F, self.H, _stream()
         gscale = 1.0
-        if self.world > 1:  # data parallel: ONE all-reduce of the flat [dW | dbh | dbv] buffer per step
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+        if self.world > 1:
+            if reduce:
+                torch.distributed.all_reduce(self.grad, group=self.pg)
             gscale = 1.0 / self.world
         self.step_count += 1
         tc = self.gemm_mode == 'tc'
         self._k('dae_optimizer_step', ptr(self.theta), ptr(self.grad), ptr(self.slot1), ptr(self.slot2), self.n_params,
                 self.opt, self.lr, self.momentum, gscale, self.step_count, ptr(getattr(self, '_ctl', None)),
-                ptr(self.W_hi) if tc else None,
-                ptr(self.W_lo) if tc else None, F, H, self.Hp, st)
+                ptr(self.W_hi) if tc else None, ptr(self.W_lo) if tc else None, F, H, self.Hp, st)
 
     # ---- explicit (anchor, pos, neg) triplets: DenoisingAutoencoderTriplet ---------------------------------------------
     def step_explicit(self, perm, offset, B, n_rows_each, stats_log_row=None):
@@ -488,17 +493,13 @@ class TrainEngine:
         stride = int(B if row_stride is None else row_stride)
         saved = (self.step_count, self.timed)
         self.timed = None
-        # warm-up outside capture (workspace allocation, function attributes, NCCL channels), on a side stream
+        # warm-up outside capture (workspace allocation, function attributes, NCCL channels)
         snap = (self.theta.clone(), None if self.slot1 is None else self.slot1.clone(), None if self.slot2 is None else self.slot2.clone(),
                 self.ctl.clone())
         self.ctl.copy_(torch.tensor([0, 0, 1, 0], dtype=torch.int64))  # warm-up / capture run on the first rows of perm_buf
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
-                call('dae_step_advance', ptr(self.ctl), stride, _stream())
-        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(2):
+            self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+            call('dae_step_advance', ptr(self.ctl), stride, _stream())
         torch.cuda.synchronize(self.device)
         self.theta.copy_(snap[0]); self.ctl.copy_(snap[3])
         if snap[1] is not None: self.slot1.copy_(snap[1])
@@ -509,15 +510,31 @@ class TrainEngine:
             self._ensure_w_split()
         torch.cuda.synchronize(self.device)
         launches0 = self.launches
+        # world == 1: one graph for the whole step.  world > 1: the NCCL all-reduce stays OUTSIDE the graphs (graph 1 = everything
+        # up to the gradients and the step's scalars, eager all-reduce, graph 2 = optimizer + cursor advance).
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
-            call('dae_step_advance', ptr(self.ctl), stride, _stream())
+        g2 = None
+        if self.world == 1:
+            with torch.cuda.graph(g):
+                self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+                call('dae_step_advance', ptr(self.ctl), stride, _stream())
+        else:
+            self._defer_update = True
+            try:
+                with torch.cuda.graph(g):
+                    self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+            finally:
+                self._defer_update = False
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                self._apply_update(reduce=False)
+                call('dae_step_advance', ptr(self.ctl), stride, _stream())
         self.graph_launches = self.launches - launches0 + 1   # kernels per replay
         self.launches = launches0
         self.step_count = saved[0]
         self.timed = saved[1]
         self._graph = g
+        self._graph2 = g2
         return g
 
     def set_step_cursor(self, offset, log_row=0):
@@ -526,6 +543,9 @@ class TrainEngine:
 
     def replay_step(self):
         self._graph.replay()
+        if self._graph2 is not None:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+            self._graph2.replay()
         self.step_count += 1
         self.launches += self.graph_launches
 
