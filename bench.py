@@ -346,8 +346,17 @@ def main():
         achieved, unit = work / dur / 1e9, 'GB/s'
         peak = peaks.get('hbm_gbs', 6650.0)
         peak_src = 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s'
+    traffic, extra = None, {}
+    try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/traffic.json)
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dominant, {})
+        traffic = tj.get('traffic_bytes')
+        extra = {k: v for k, v in tj.items() if k != 'traffic_bytes'}
+    except (OSError, ValueError):
+        pass
     roofline = {'kernel': dominant, 'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': unit, 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'avg_launch_ms': dur * 1e3,
+                'traffic': traffic, 'algorithmic_work': work, 'ncu': extra, 'peak_source': peak_src,
+                'note': ('algorithmic FLOPs = 2*M*N*K; the kernel executes 3x that as bf16 MMAs (hi/lo split) for fp32 parity'
+                         if bound == 'tensor' else ''), 'avg_launch_ms': dur * 1e3,
                 'share_of_step': float(np.mean(dom_ms)) / (ms / K), 'launches_per_step': float(gpu_launches) / K}
 
     if rank != 0:

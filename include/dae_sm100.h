@@ -233,6 +233,19 @@ int dae_optimizer_step(float* theta, const float* grad, float* slot1, float* slo
 int dae_mask_values(const float* values, const uint8_t* keep, int64_t nnz, float corr_frac, uint64_t seed,
                     uint64_t epoch, float* values_out, void* stream);
 
+/* ---- "next" row: pairwise similarity of embeddings + nearest-article lookup -----------------
+ * Replaces helpers.pairwise_similarity (helpers.py:11-50: sklearn cosine_similarity / linear_kernel, optional normalize,
+ * zeroed diagonal) and the nanargmax lookup of main_autoencoder.py:352-353.  sim = normalize(E).normalize(E)^T runs on
+ * dae_gemm_bf16x3; these are the two kernels around it.
+ * dae_rownorm_split_bf16: rows scaled by 1/||x||_2 (norm_kind 2; all-zero rows untouched, like sklearn), 1/||x||_1 (1),
+ *   1/max|x| (3) or 1 (0), written as bf16 hi/lo [rows x ld_dst] (zero padded) and/or as fp32 x_out.
+ * dae_row_argmax: per row arg-max / max of S skipping column row+diag_offset (optionally zeroing it in place).
+ */
+int dae_rownorm_split_bf16(const float* X, int32_t rows, int32_t cols, int64_t ld, int32_t norm_kind, void* hi, void* lo,
+                           int64_t ld_dst, float* x_out, int64_t ld_out, void* stream);
+int dae_row_argmax(float* S, int32_t rows, int32_t cols, int64_t ld, int64_t diag_offset, int32_t zero_diag,
+                   int32_t* idx_out, float* val_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
