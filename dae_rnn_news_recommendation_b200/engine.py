@@ -132,6 +132,8 @@ class TrainEngine:
         if self.H > (1024 if self.H % 4 == 0 else (512 if self.H % 2 == 0 else 256)):
             self.enc_bwd_mode = 'atomic'
         self._ent_cap = 0
+        self.fork_branches = os.environ.get('DAE_FORK', '1') == '1'
+        self._side = None
         self.Hp = (self.H + 1 + 63) // 64 * 64   # K padding of E / W (+1: the all-ones column that turns dW into [dW | dbv])
         self.Fp = (self.F + 31) // 32 * 32
         self.in_scale = 1.0  # decay noise folds into the encode kernels (utils.decay_noise, autoencoder/utils.py:147-159)
@@ -261,6 +263,7 @@ class TrainEngine:
             self.col_start = torch.zeros(self.F + 1, **i32)
             self.col_cursor = torch.zeros(self.F, **i32)
         if cap > self._ent_cap:
+            cap = int(cap * 1.5) if c.max_row_nnz is None else cap   # per-step host feeds vary in size: grow geometrically
             self._graph = None
             self.ent_col = torch.empty(cap, dtype=torch.int32, device=self.device)
             self.ent_row = torch.empty(cap, dtype=torch.int32, device=self.device)
@@ -332,28 +335,53 @@ class TrainEngine:
         if tc:  # operands of the tensor-core contractions: E (with the all-ones column) and W as bf16 hi/lo pairs
             self._tc_split(self.E, B, H, H, self.E_hi, self.E_lo, ones_col=H)
             self._ensure_w_split()
-        if strat != 0:
-            if tc:
-                Ehl = (self.E_hi, self.E_lo)
-                self._tc_gemm(B, B, H, 1.0, Ehl, 0, Ehl, 0, self.S, B, tag='gemm_gram')
-            else:
-                self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
-            if strat == 1:
-                self._k('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
-                        ptr(self.stats), 0, st)
-            else:
-                self._k('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
-                        ptr(self.stats), st, n_launch=2)
+        # batch_all: the mining branch (Gram matrix -> triplet sweep -> G + G^T) does not feed the decode branch (the data
+        # weights are closed-form), so the two run as parallel branches (second stream; parallel nodes once graph-captured) and
+        # the short mining CTAs fill the tails of the persistent GEMM kernels.  batch_hard's weights come out of the mining
+        # kernel, so there the order stays sequential.
+        fork = tc and strat == 1 and train and self.fork_branches
+        if fork:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                self._mining(B, strat, tc)
+                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), _stream())
+                ev2 = torch.cuda.Event()
+                ev2.record(self._side)
+        elif strat != 0:
+            self._mining(B, strat, tc)
         self._decode_and_backward(B, self.rows, self.weight if strat != 0 else None, train)
+        if fork:
+            torch.cuda.current_stream().wait_event(ev2)
         if strat != 0 and train:  # dE += alpha (G + G^T) E
             if tc:
-                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), st)
+                if not fork:
+                    self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), st)
                 self._tc_gemm(B, H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE, H, accumulate=1,
                               tag='gemm_dE_tri')
             else:
                 self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
                 self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
         self._encode_backward_and_update(B, self.rows, self.weight if strat != 0 else None, strat, stats_log_row, train)
+
+    def _mining(self, B, strat, tc):
+        """S = E.E^T and the triplet kernel (loss, statistics, G = dL/dS; batch_hard: also the data weights)."""
+        H, st = self.H, _stream()
+        if tc:
+            Ehl = (self.E_hi, self.E_lo)
+            self._tc_gemm(B, B, H, 1.0, Ehl, 0, Ehl, 0, self.S, B, tag='gemm_gram')
+        else:
+            self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
+        if strat == 1:
+            self._k('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
+                    ptr(self.stats), 0, st)
+        else:
+            self._k('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
+                    ptr(self.stats), st, n_launch=2)
 
     def evaluate(self, csr, labels, B=None):
         """Forward-only cost of the whole set fed as ONE batch with x_corr = x, like the reference's validation pass
