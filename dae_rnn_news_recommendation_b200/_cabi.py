@@ -31,7 +31,8 @@ _SIGNATURES = {
     'dae_last_error': (C.c_int, [C.c_char_p, sz]),
     'dae_batch_prepare': (C.c_int, [p, i64, p, i32, p, i32, p, p, p, p, p, p, p]),
     'dae_step_advance': (C.c_int, [p, i64, p]),
-    'dae_encode_csr_fwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p]),
+    'dae_encode_csr_fwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p, i64, p]),
+    'dae_col_scan': (C.c_int, [p, i32, p, p, p]),
     'dae_encode_csr_bwd_gather': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p, p, p, p, p, p, p]),
     'dae_encode_csr_bwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p]),
     'dae_sgemm': (C.c_int, [i32, i32, i32, f32, p, i64, i64, p, i64, i64, f32, p, i64, p]),

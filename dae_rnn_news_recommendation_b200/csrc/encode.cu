@@ -7,6 +7,7 @@
 // chunks of 128 with masked (zero) entries compacted away, then every thread gathers its 128-bit slice of W[col,:]
 // with read-only vector loads, several rows of W in flight per thread.  W (20 MB at F=10k,H=500) is L2 resident,
 // so the gather runs at L2 bandwidth; HBM only sees the CSR stream, W once, and the E write.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace dae {
@@ -50,7 +51,8 @@ template <int ACT, int VW, int NC>
 __global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
     const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ W, const float* __restrict__ bh,
-    float* __restrict__ E, int64_t ldE, int32_t* __restrict__ col_count) {
+    float* __restrict__ E, int64_t ldE, int32_t* __restrict__ col_count, __nv_bfloat16* __restrict__ e_hi,
+    __nv_bfloat16* __restrict__ e_lo, int64_t ld_split) {
   __shared__ int s_col[kEncThreads];
   __shared__ float s_val[kEncThreads];
   __shared__ int s_wcnt[kEncThreads / 32];
@@ -93,7 +95,13 @@ __global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
 #pragma unroll
       for (int e = 0; e < VW; ++e) {
         const float b = __ldg(bh + hcol[c] + e);
-        E[(int64_t)r * ldE + hcol[c] + e] = act_fwd<ACT>(acc[c][e] + b) - act_fwd<ACT>(b);
+        const float ev = act_fwd<ACT>(acc[c][e] + b) - act_fwd<ACT>(b);
+        E[(int64_t)r * ldE + hcol[c] + e] = ev;
+        if (e_hi != nullptr) {  // bf16 hi/lo operand copy for the tensor-core contractions (fuses dae_split_bf16 of E)
+          const __nv_bfloat16 h = __float2bfloat16_rn(ev);
+          e_hi[(int64_t)r * ld_split + hcol[c] + e] = h;
+          e_lo[(int64_t)r * ld_split + hcol[c] + e] = __float2bfloat16_rn(ev - __bfloat162float(h));
+        }
       }
     }
   }
@@ -322,12 +330,12 @@ __global__ void __launch_bounds__(kEncThreads) encode_bwd_gather_kernel(const in
 template <int ACT, int VW>
 static int launch_fwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
                          const int32_t* rows, int H, float in_scale, const float* W, const float* bh, float* E, int64_t ldE,
-                         int32_t* col_count) {
+                         int32_t* col_count, void* e_hi, void* e_lo, int64_t ld_split) {
   switch (nc) {
-    case 1: encode_fwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
-    case 2: encode_fwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
-    case 4: encode_fwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
-    default: encode_fwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count); break;
+    case 1: encode_fwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
+    case 2: encode_fwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
+    case 4: encode_fwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
+    default: encode_fwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
   }
   return 0;
 }
@@ -362,10 +370,12 @@ static inline int pick_nc(int H, int vw) {
 
 extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
                                   int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* W, const float* bh,
-                                  int32_t enc_act, float* E, int64_t ldE, int32_t* col_count, void* stream) {
+                                  int32_t enc_act, float* E, int64_t ldE, int32_t* col_count, void* e_hi, void* e_lo,
+                                  int64_t ld_split, void* stream) {
   using namespace dae;
   DAE_REQUIRE(indptr && indices && values && W && bh && E, "dae_encode_csr_fwd: null pointer");
   DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_fwd: bad shape n_rows=%d F=%d H=%d ldE=%lld", n_rows, F, H, (long long)ldE);
+  DAE_REQUIRE(!e_hi || (e_lo && ld_split >= H), "dae_encode_csr_fwd: bad split outputs");
   if (n_rows == 0) return DAE_OK;
   const int vw = pick_vw(H, H, W);
   const int nc = pick_nc(H, vw);
@@ -374,9 +384,9 @@ extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices,
   if (col_count) DAE_CUDA(cudaMemsetAsync(col_count, 0, sizeof(int32_t) * F, st));
   dim3 grid(n_rows);
   DAE_DISPATCH_ACT(enc_act, ACT, {
-    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count);
-    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count);
-    else launch_fwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count);
+    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
+    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
+    else launch_fwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
   });
   DAE_CHECK_LAUNCH("dae_encode_csr_fwd");
   return DAE_OK;
@@ -410,7 +420,7 @@ extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* i
                                          int32_t* col_start, int32_t* col_cursor, int32_t* ent_col, int32_t* ent_row,
                                          float* ent_val, void* stream) {
   using namespace dae;
-  DAE_REQUIRE(indptr && indices && values && E && bh && dE && dW && dbh && col_count && col_start && col_cursor && ent_col && ent_row && ent_val,
+  DAE_REQUIRE(indptr && indices && values && E && bh && dE && dW && dbh && col_start && col_cursor && ent_col && ent_row && ent_val,
               "dae_encode_csr_bwd_gather: null pointer");
   DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_bwd_gather: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -420,7 +430,7 @@ extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* i
   if (pick_vw(H, H, dW) < vw) vw = pick_vw(H, H, dW);
   const int nc = pick_nc(H, vw);
   if (nc < 0 || nc > 2) { set_error("dae_encode_csr_bwd_gather: H=%d not supported (use dae_encode_csr_bwd)", H); return DAE_ERR_UNSUPPORTED; }
-  col_scan_kernel<<<1, 1024, 0, st>>>(col_count, F, col_start, col_cursor);
+  if (col_count) col_scan_kernel<<<1, 1024, 0, st>>>(col_count, F, col_start, col_cursor);  // NULL: dae_col_scan already ran
   DAE_DISPATCH_ACT(enc_act, ACT, {
     encode_bwd_rows_kernel<ACT><<<n_rows, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dbh, col_cursor,
                                                                ent_col, ent_row, ent_val);
@@ -432,5 +442,13 @@ extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* i
 #undef DAE_GATHER_NC
 #undef DAE_GATHER
   DAE_CHECK_LAUNCH("dae_encode_csr_bwd_gather");
+  return DAE_OK;
+}
+
+extern "C" int dae_col_scan(const int32_t* col_count, int32_t F, int32_t* col_start, int32_t* col_cursor, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(col_count && col_start && col_cursor && F > 0, "dae_col_scan: bad arguments");
+  col_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(col_count, F, col_start, col_cursor);
+  DAE_CHECK_LAUNCH("dae_col_scan");
   return DAE_OK;
 }

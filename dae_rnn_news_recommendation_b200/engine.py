@@ -239,8 +239,9 @@ class TrainEngine:
         if self.gemm_mode == 'tc':
             bf = dict(dtype=torch.bfloat16, device=self.device)
             self.Bp = (B + 7) // 8 * 8
-            self.E_hi = torch.empty(B, self.Hp, **bf)
-            self.E_lo = torch.empty(B, self.Hp, **bf)
+            self.E_hi = torch.zeros(B, self.Hp, **bf)   # columns [H+1, Hp) stay zero, column H is the all-ones column
+            self.E_lo = torch.zeros(B, self.Hp, **bf)
+            self.E_hi[:, self.H] = 1.0
             self.dZ_hi = torch.empty(B, self.Fp, **bf)
             self.dZ_lo = torch.empty(B, self.Fp, **bf)
             self.loss_parts = torch.empty(2 * ((self.F + 255) // 256), B, **f32)
@@ -329,11 +330,12 @@ class TrainEngine:
         gather = train and self.enc_bwd_mode == 'gather'
         if gather:
             self._ensure_bucket_scratch(B)
-        self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
-                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None, st)
         tc = self.gemm_mode == 'tc'
-        if tc:  # operands of the tensor-core contractions: E (with the all-ones column) and W as bf16 hi/lo pairs
-            self._tc_split(self.E, B, H, H, self.E_hi, self.E_lo, ones_col=H)
+        # the kernel also emits E as the bf16 hi/lo pair (plus the all-ones column kept in E_hi) the tensor-core GEMMs consume
+        self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None,
+                ptr(self.E_hi) if tc else None, ptr(self.E_lo) if tc else None, self.Hp, st)
+        if tc:
             self._ensure_w_split()
         # batch_all: the mining branch (Gram matrix -> triplet sweep -> G + G^T) does not feed the decode branch (the data
         # weights are closed-form), so the two run as parallel branches (second stream; parallel nodes once graph-captured) and
@@ -348,6 +350,9 @@ class TrainEngine:
             ev.record(main)
             self._side.wait_event(ev)
             with torch.cuda.stream(self._side):
+                if gather:   # the column-bucket offsets of the backward gather only need the forward kernel's counts
+                    self._k('dae_col_scan', ptr(self.col_count), F, ptr(self.col_start), ptr(self.col_cursor), _stream())
+                    self._scan_done = True
                 self._mining(B, strat, tc)
                 self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), _stream())
                 ev2 = torch.cuda.Event()
@@ -445,8 +450,11 @@ class TrainEngine:
         F, H, st = self.F, self.H, _stream()
         c = self.csr_c
         if train and self.enc_bwd_mode == 'gather':
+            scan_done = getattr(self, '_scan_done', False)
+            self._scan_done = False
             self._k('dae_encode_csr_bwd_gather', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
-                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), ptr(self.col_count),
+                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()),
+                    None if scan_done else ptr(self.col_count),
                     ptr(self.col_start), ptr(self.col_cursor), ptr(self.ent_col), ptr(self.ent_row), ptr(self.ent_val), st, n_launch=3,
                     tag='dae_encode_csr_bwd')
         elif train:
@@ -489,9 +497,9 @@ class TrainEngine:
         if gather:
             self._ensure_bucket_scratch(B3)
         self._k('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H,
-                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None, st)
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None,
+                ptr(self.E_hi) if self.gemm_mode == 'tc' else None, ptr(self.E_lo) if self.gemm_mode == 'tc' else None, self.Hp, st)
         if self.gemm_mode == 'tc':
-            self._tc_split(self.E, B3, H, H, self.E_hi, self.E_lo, ones_col=H)
             self._ensure_w_split()
         self._decode_and_backward(B3, self.rows, None)
         E, d = self.E, self.dE
@@ -506,7 +514,7 @@ class TrainEngine:
         if out is None:
             out = torch.empty(N, self.H, dtype=torch.float32, device=self.device)
         self._k('dae_encode_csr_fwd', ptr(csr.indptr), ptr(csr.indices), ptr(csr.values if values is None else values), None,
-                N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, None, _stream(),
+                N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, None, None, None, 0, _stream(),
                 tag='encode_transform')
         return out
 

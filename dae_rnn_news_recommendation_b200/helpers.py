@@ -81,7 +81,7 @@ def _pairwise_sparse(m, norm, metric, set_diagonal_zero, device):
     out = torch.empty(n, n, dtype=torch.float32, device=device)
     zero_b = torch.zeros(n, dtype=torch.float32, device=device)
     call('dae_encode_csr_fwd', csr.indptr.data_ptr(), csr.indices.data_ptr(), csr.values.data_ptr(), None, n, f, n, 1.0,
-         dense_t.data_ptr(), zero_b.data_ptr(), _cabi.ACT['none'], out.data_ptr(), n, None, _stream())
+         dense_t.data_ptr(), zero_b.data_ptr(), _cabi.ACT['none'], out.data_ptr(), n, None, None, None, 0, _stream())
     if set_diagonal_zero:
         out.diagonal().zero_()
     return out.cpu().numpy()

@@ -92,11 +92,13 @@ int dae_batch_prepare(const int32_t* perm, int64_t offset, const int64_t* ctl, i
  * E is written fp32 with leading dimension ldE.  Entries whose value is exactly 0 (masked) are skipped.
  * col_count (optional, int32[F]): zeroed, then receives the number of kept entries per feature column of the batch --
  * the bucket sizes dae_encode_csr_bwd_gather needs.
+ * e_hi / e_lo (optional, bf16 [n_rows x ld_split]): columns [0, H) of the bf16 hi/lo operand copy of E for the tensor-core
+ * GEMMs (the caller keeps the padding columns zero and the all-ones column set).
  */
 int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const float* values,
                        const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
                        const float* W, const float* bh, int32_t enc_act, float* E, int64_t ldE,
-                       int32_t* col_count, void* stream);
+                       int32_t* col_count, void* e_hi, void* e_lo, int64_t ld_split, void* stream);
 
 /* ---- K5: encode backward -------------------------------------------------------------------------
  * dA = dE * f'(A);  dbh = sum_i dA_i - f'(bh) * sum_i dE_i;  dW[c,:] += v * dA[r,:] for every stored
@@ -114,6 +116,9 @@ int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const floa
  * list, accumulate v * dA[r,:] in registers per column run and issue one vector red.global.add per (chunk, column) run.
  * Supports H <= 1024 (H % 4 == 0) / 512 (H % 2 == 0) / 256; larger H: use dae_encode_csr_bwd.
  */
+/* exclusive scan of the per-column counts into col_start[F+1] / col_cursor[F]; dae_encode_csr_bwd_gather runs it itself unless
+ * it is called with col_count == NULL (then the scan must already have been issued, e.g. on a parallel stream) */
+int dae_col_scan(const int32_t* col_count, int32_t F, int32_t* col_start, int32_t* col_cursor, void* stream);
 int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* indices, const float* values,
                               const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
                               const float* E, const float* bh, int32_t enc_act, float* dE, int64_t ldE, float* dW,
