@@ -41,6 +41,7 @@ _SIGNATURES = {
     'dae_gemm_bf16x3': (C.c_int, [i32, i32, i32, f32, p, p, i64, i32, p, p, i64, i32, p, i64, i32, i32, p, i32, i32, p]),
     'dae_gemm_bf16x3_tune': (C.c_int, [i32, p, i32, i32, i32, f32, p, p, i64, i32, p, p, i64, i32, p, i64, i32, i32, p, i32, i32, p]),
     'dae_debug_set_trace': (C.c_int, [p]),
+    'dae_gemm_set_cluster_mode': (C.c_int, [i32]),
     'dae_decode_fused_bf16x3': (C.c_int, [i32, i32, i32, p, p, i64, p, p, i64, p, p, p, p, p, i32, i32, p, p, p, p, i64, p, p, p]),
     'dae_reduce_parts': (C.c_int, [p, i32, i32, p, p]),
     'dae_decode_loss_bwd': (C.c_int, [p, p, p, p, i32, i32, p, i32, i32, p, p, p, i64, p, p]),

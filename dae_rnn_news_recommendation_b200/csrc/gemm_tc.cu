@@ -68,6 +68,24 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset of every CTA in cta_mask and completes tx on each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit that arrives on the mbarrier at this smem offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -174,7 +192,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
+// CL = 2: two CTAs of a cluster work on tiles (2*mp, nb) and (2*mp+1, nb): they share the B tile, each loads half of it and TMA
+// multicasts it into both CTAs' shared memory (1/3 less L2 -> SM operand traffic); MMAs stay cta_group::1, the stage-free
+// (empty) barriers collect one tcgen05.commit from each CTA.
+template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS, int CL>
 __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore), 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                                                                       const __grid_constant__ CUtensorMap tm_a_lo,
                                                                       const __grid_constant__ CUtensorMap tm_b_hi,
@@ -195,17 +216,22 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
   __shared__ __align__(16) uint8_t s_stage[EPI == EPI_DECODE ? kEpiWarps : 1][2][32][48];  // bf16 hi / lo dZ blocks [32 rows x 16 cols], rows padded to 48 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per_split = (kblocks_total + p.k_splits - 1) / p.k_splits;
+  // work items are (m-tile group of CL tiles, n tile, k split); the CTAs of a cluster take the CL m-tiles of one group.
+  // A CTA whose m-tile is past the end still runs the pipeline (TMA zero-fills, the epilogue stores nothing).
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int tiles_m = (((p.M + BLOCK_M - 1) / BLOCK_M) + CL - 1) / CL;   // m-tile GROUPS
   const int n_work = tiles_m * tiles_n * p.k_splits;
+  const int w_begin = blockIdx.x / CL, w_step = gridDim.x / CL;
+#define DAE_MB(w) (((w) % tiles_m) * CL + (int)crank)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiWarps); }
     fence_barrier_init();
   }
@@ -214,7 +240,7 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before anything multicasts
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -222,8 +248,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int mb = w % tiles_m, nb = (w / tiles_m) % tiles_n, ks = w / (tiles_m * tiles_n);
+      for (int w = w_begin; w < n_work; w += w_step) {
+        const int mb = DAE_MB(w), nb = (w / tiles_m) % tiles_n, ks = w / (tiles_m * tiles_n);
         const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -242,14 +268,29 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
               tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mb * BLOCK_M + j * 64, kb * BLOCK_K);
             }
           }
-          if (!p.b_mn) {
-            tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, nb * BLOCK_N);
-            tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, nb * BLOCK_N);
-          } else {
+          if (CL == 1) {
+            if (!p.b_mn) {
+              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, nb * BLOCK_N);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, nb * BLOCK_N);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j) {
-              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
-              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+              for (int j = 0; j < BLOCK_N / 64; ++j) {
+                tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+                tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+              }
+            }
+          } else {   // this CTA fetches its half of the shared B tile and multicasts it to both CTAs of the cluster
+            constexpr int HN = BLOCK_N / 2;
+            if (!p.b_mn) {   // the B tensor maps of the cluster variant carry a box of BLOCK_N / 2 rows
+              tma_load_2d_mc(&tm_b_hi, &full_bar[stage], sb_hi + crank * HN * 128, kb * BLOCK_K, nb * BLOCK_N + crank * HN, 0x3);
+              tma_load_2d_mc(&tm_b_lo, &full_bar[stage], sb_lo + crank * HN * 128, kb * BLOCK_K, nb * BLOCK_N + crank * HN, 0x3);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < HN / 64; ++jj) {
+                const int j = crank * (HN / 64) + jj;
+                tma_load_2d_mc(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K, 0x3);
+                tma_load_2d_mc(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K, 0x3);
+              }
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -264,7 +305,7 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
       int acc = 0; uint32_t acc_phase = 0;
       long long* trace = (blockIdx.x == 0) ? p.trace : nullptr;
       int tr_i = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      for (int w = w_begin; w < n_work; w += w_step) {
         const int ks = w / (tiles_m * tiles_n);
         const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
         if (trace && tr_i < 500) trace[tr_i++] = clock64();
@@ -291,7 +332,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
             umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
             umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
           }
-          umma_commit(&empty_bar[stage]);                   // frees this smem stage when the MMAs retire
+          if (CL == 1) umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
+          else umma_commit_mc(&empty_bar[stage], 0x3);      // ... in BOTH CTAs: the peer's multicast writes into this stage too
           if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -308,8 +350,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     int acc = 0; uint32_t acc_phase = 0;
     long long* trace = (blockIdx.x == 0 && ew == 0 && lane == 0) ? p.trace : nullptr;
     int tr_i = 500;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int mb = w % tiles_m, nb = (w / tiles_m) % tiles_n;
+    for (int w = w_begin; w < n_work; w += w_step) {
+      const int mb = DAE_MB(w), nb = (w / tiles_m) % tiles_n;
       const int m = mb * BLOCK_M + row_in_tile;
       const int n0 = nb * BLOCK_N + half * HALF_N;
       if (EPI == EPI_DECODE) {  // stage this tile's visible-bias slice (named barrier 1: the epilogue threads)
@@ -494,11 +536,12 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer may still multicast / arrive here
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
+#undef DAE_MB
 }
 
 // tile_ptr[m][t] = number of stored entries of batch row m with column < t * half_n (t = 0 .. n_half_tiles): where each
@@ -591,8 +634,12 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t o
 
 struct Operand { const void* hi; const void* lo; int64_t ld; int mn_major; };
 
+static int g_cluster_mode = -1;   // -1: read DAE_GEMM_CLUSTER on first use; 0 = single-CTA tiles; 1 = 2-CTA clusters with B multicast
+
 template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
 static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStream_t st) {
+  if (g_cluster_mode < 0) { const char* e = getenv("DAE_GEMM_CLUSTER"); g_cluster_mode = (e && e[0] == '1') ? 1 : 0; }
+  const bool cl2 = (g_cluster_mode == 1) && (BLOCK_N == 256);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   // K-major: tensor [rows=MN x cols=K], box {64 k, tile rows};  MN-major: tensor [rows=K x cols=MN], box {64 mn, 64 k}
@@ -604,21 +651,37 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
     if ((rc = make_map(&ta_lo, A.lo, p.M, p.K, A.ld, 64))) return rc;
   }
   if (!B.mn_major) {
-    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, BLOCK_N))) return rc;
-    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, BLOCK_N))) return rc;
+    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, cl2 ? BLOCK_N / 2 : BLOCK_N))) return rc;
+    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, cl2 ? BLOCK_N / 2 : BLOCK_N))) return rc;
   } else {
     if ((rc = make_map(&tb_hi, B.hi, p.N, p.K, B.ld, 64))) return rc;
     if ((rc = make_map(&tb_lo, B.lo, p.N, p.K, B.ld, 64))) return rc;
   }
   p.a_mn = A.mn_major; p.b_mn = B.mn_major;
   constexpr int smem = STAGES * (2 * BLOCK_M * BLOCK_K * 2 + 2 * BLOCK_N * BLOCK_K * 2) + 1024;
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS>;
-  static bool attr = false;
-  if (!attr) { DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-  const int tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.k_splits;
-  int sms = 148;
-  const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore), smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  constexpr int threads = tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore);
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  if (!cl2) {
+    auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS, 1>;
+    static bool attr = false;
+    if (!attr) { DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    const int tiles = tiles_m * tiles_n * p.k_splits;
+    const int grid = tiles < 148 ? tiles : 148;
+    kern<<<grid, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  } else {
+    auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS, 2>;
+    static bool attr = false;
+    if (!attr) { DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    const int groups = ((tiles_m + 1) / 2) * tiles_n * p.k_splits;
+    const int clusters = groups < 74 ? groups : 74;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    DAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  }
   return DAE_OK;
 }
 
@@ -629,6 +692,8 @@ using namespace dae;
 static long long* g_debug_trace = nullptr;
 // diagnostic: the next tcgen05 launches write a clock64 trace of CTA 0 (MMA issuer at [0,500), epilogue warp 0 at [500,1000))
 extern "C" int dae_debug_set_trace(void* trace) { g_debug_trace = (long long*)trace; return DAE_OK; }
+// 0 = single-CTA tiles (default), 1 = 2-CTA clusters sharing the B tile through TMA multicast (128 x 256 tiles only)
+extern "C" int dae_gemm_set_cluster_mode(int32_t mode) { dae::g_cluster_mode = mode ? 1 : 0; return DAE_OK; }
 
 extern "C" int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo, int64_t ld_dst,
                               int32_t ones_col, float scale, void* stream) {

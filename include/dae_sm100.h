@@ -169,6 +169,9 @@ int dae_gemm_bf16x3_tune(int32_t variant, void* trace, int32_t M, int32_t N, int
                          int32_t k_splits, int32_t accumulate, void* stream);
 /* diagnostic: subsequent fused-decode launches write a clock64 trace of CTA 0 into trace (int64[1000] device buffer; NULL = off) */
 int dae_debug_set_trace(void* trace);
+/* 128x256-tile launches: 0 = one CTA per tile (default; also env DAE_GEMM_CLUSTER=0), 1 = clusters of two CTAs that share the
+ * B tile, each fetching half of it and TMA-multicasting it to both (1/3 less L2->SM operand traffic) */
+int dae_gemm_set_cluster_mode(int32_t mode);
 int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
                             int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
                             const int64_t* indptr, const int32_t* indices, const float* values,
