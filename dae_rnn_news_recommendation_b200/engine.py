@@ -244,7 +244,6 @@ class TrainEngine:
             self.E_hi[:, self.H] = 1.0
             self.dZ_hi = torch.empty(B, self.Fp, **bf)
             self.dZ_lo = torch.empty(B, self.Fp, **bf)
-            self.loss_parts = torch.empty(2 * ((self.F + 255) // 256), B, **f32)
             self.tile_ptr = torch.empty(B, 4 * ((self.F + 255) // 256) + 1, **i32)
             if not hasattr(self, 'W_hi'):
                 self.W_hi = torch.empty(self.F, self.Hp, **bf)
@@ -403,7 +402,6 @@ class TrainEngine:
     def _decode_and_backward(self, B, rows, weight, train=True):
         F, H, st = self.F, self.H, _stream()
         c = self.csr
-        self._loss_parts_live = None
         if self.gemm_mode == 'tc':
             return self._decode_and_backward_tc(B, rows, weight, train)
         self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F, tag='gemm_decode_fwd')  # Z = E.W^T
@@ -426,9 +424,7 @@ class TrainEngine:
                     self.Hp, ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), ptr(self.bv), self.dec_act, self.loss,
                     ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.row_loss), ptr(self.tile_ptr), st,
                     n_launch=2, tag='gemm_decode_fwd')
-            self._loss_parts_live = None
-        else:
-            self._loss_parts_live = None  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
+        else:  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
             self._tc_gemm(B, F, H, 1.0, Ehl, 0, Whl, 0, self.Z, F, tag='gemm_decode_fwd')
             self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
                     self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
@@ -460,8 +456,7 @@ class TrainEngine:
         elif train:
             self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
                     ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
-        parts = getattr(self, '_loss_parts_live', None)   # fused decode epilogue: per-tile partial row losses
-        self._k('dae_step_finalize', ptr(self.row_loss), ptr(parts), 0 if parts is None else parts.shape[0], ptr(weight), B, strat,
+        self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(weight), B, strat,
                 self.alpha, ptr(self.stats), ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
         if not train or getattr(self, '_defer_update', False):
             return

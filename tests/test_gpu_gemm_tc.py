@@ -104,3 +104,25 @@ def test_fused_decode_matches_unfused(loss, dec):
     dz = (dzh.float() + dzl.float())[:, :F]
     assert rel_err(dz.cpu().numpy(), Z.cpu().numpy()) < 3e-5
     assert float(dzh[:, F:].float().abs().max()) == 0.0
+
+
+def test_reduce_parts_and_finalize_with_partials():
+    """dae_reduce_parts and the `parts` input of dae_step_finalize give the same weighted mean as a plain row-loss vector."""
+    from dae_rnn_news_recommendation_b200 import _cabi
+    B, P = 300, 7
+    st = torch.cuda.current_stream().cuda_stream
+    parts = torch.rand(P, B, device=DEV)
+    w = torch.rand(B, device=DEV) * 3
+    rl = torch.empty(B, device=DEV)
+    _cabi.call('dae_reduce_parts', parts.data_ptr(), P, B, rl.data_ptr(), st)
+    assert torch.allclose(rl, parts.sum(0), rtol=1e-6)
+    out = []
+    for use_parts in (False, True):
+        stats = torch.zeros(16, dtype=torch.float64, device=DEV)
+        stats[_cabi.STAT['sum_w']] = float(w.double().sum())
+        _cabi.call('dae_step_finalize', None if use_parts else rl.data_ptr(), parts.data_ptr() if use_parts else None, P if use_parts else 0,
+                   w.data_ptr(), B, 0, 1.0, stats.data_ptr(), None, None, st)
+        torch.cuda.synchronize()
+        out.append(float(stats[_cabi.STAT['ae_loss']]))
+    want = float((parts.sum(0).double() * w.double()).sum() / w.double().sum())
+    assert abs(out[0] - want) < 1e-6 * abs(want) and abs(out[1] - want) < 1e-6 * abs(want)

@@ -214,3 +214,58 @@ def test_graph_replay_matches_eager_steps(gemm_mode):
     assert rel_err(res[1][0][:, STAT['triplet_loss']], res[0][0][:, STAT['triplet_loss']]) < 1e-5
     assert rel_err(res[1][1]['enc_w'], res[0][1]['enc_w']) < 5e-3  # adam (see _run_step_pair)
     assert rel_err(res[1][1]['dec_b'], res[0][1]['dec_b']) < 5e-3
+
+
+def test_corrupted_copy_with_its_own_structure(gemm_mode):
+    """salt-and-pepper noise ADDS entries, so the corrupted matrix is a second CSR (encode reads it, the loss reads the clean one)."""
+    from dae_rnn_news_recommendation_b200.engine import DeviceCSR
+    from dae_rnn_news_recommendation_b200.autoencoder import utils
+    F, H, B = 300, 24, 80
+    x = random_csr(B, F, 12, seed=51)
+    np.random.seed(3)
+    xc = utils.salt_and_pepper_noise(x, 9)
+    assert xc.nnz != x.nnz
+    labels = np.random.default_rng(52).integers(0, 3, B).astype(np.float32)
+    W0 = xavier(F, H, 53) * 3
+    kw = dict(enc_act_func='sigmoid', dec_act_func='sigmoid', loss_func='cross_entropy', opt='gradient_descent', learning_rate=0.05,
+              triplet_strategy='batch_hard')
+    eng = _engine(F, H, **kw)
+    eng.set_parameters(W0)
+    eng.set_data(DeviceCSR(x, eng.device), None, torch.from_numpy(labels).to(eng.device), csr_corrupt=DeviceCSR(xc, eng.device))
+    eng.step(None, 0, B)
+    torch.cuda.synchronize()
+    o = _oracle(W0, **kw).step(x, xc, labels)
+    st = eng.read_stats()
+    assert rel_err(st['cost'], o['cost']) < REL_TOL and rel_err(st['triplet_loss'], o['triplet_loss']) < REL_TOL
+    g = eng.grad.cpu().numpy()
+    assert rel_err(g[:F * H].reshape(F, H), o['grads'][0]) < REL_TOL
+
+
+def test_triplet_estimator_fit(gemm_mode):
+    """DenoisingAutoencoderTriplet.fit on {'org','pos','neg'}: first step == oracle step on the same rows, loss falls, transform works."""
+    from dae_rnn_news_recommendation_b200.autoencoder import DenoisingAutoencoderTriplet
+    from dae_rnn_news_recommendation_b200._cabi import STAT
+    N, F = 120, 200
+    data = {k: random_csr(N, F, 10, seed=s) for k, s in (('org', 61), ('pos', 62), ('neg', 63))}
+    W0 = xavier(F, 20, 64) * 3
+    m = DenoisingAutoencoderTriplet(model_name='t', main_dir='t', compress_factor=10, enc_act_func='sigmoid', dec_act_func='sigmoid',
+                                    loss_func='cross_entropy', num_epochs=3, batch_size=40.0, opt='gradient_descent', learning_rate=0.05,
+                                    corr_type='none', verbose=False, verbose_step=1, seed=5, alpha=2, W_init=W0)
+    m.fit(data)
+    assert len(m.train_cost_batch[0]) == 3 and np.isfinite(m.train_cost_batch[0]).all()
+    emb = m.transform(data['org'])
+    assert emb.shape == (N, 20) and np.isfinite(emb).all()
+    # replay the first step on the oracle: same seed -> same shuffle (no corruption draws with corr_type none)
+    np.random.seed(5)
+    order = list(range(N)); np.random.shuffle(order)
+    idx = order[:40]
+    orc = _oracle(W0, enc_act_func='sigmoid', dec_act_func='sigmoid', loss_func='cross_entropy', opt='gradient_descent',
+                  learning_rate=0.05, alpha=2.0, triplet_strategy='none')
+    o = orc.step_explicit([data[k][idx] for k in ('org', 'pos', 'neg')], [data[k][idx] for k in ('org', 'pos', 'neg')])
+    # first epoch's first step is the first row of the (last) epoch log only if num_epochs == 1 -> refit one epoch
+    m1 = DenoisingAutoencoderTriplet(model_name='t1', main_dir='t1', compress_factor=10, enc_act_func='sigmoid', dec_act_func='sigmoid',
+                                     loss_func='cross_entropy', num_epochs=1, batch_size=40.0, opt='gradient_descent', learning_rate=0.05,
+                                     corr_type='none', verbose=False, verbose_step=1, seed=5, alpha=2, W_init=W0)
+    m1.fit(data)
+    assert rel_err(m1.train_cost_batch[0][0], o['cost']) < REL_TOL
+    assert rel_err(m1.train_cost_batch[2][0], o['triplet_loss']) < REL_TOL
