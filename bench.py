@@ -307,12 +307,14 @@ def main():
     from dae_rnn_news_recommendation_b200.autoencoder import utils as hostutils
     Ke = min(K, 20)
     rng = np.random.RandomState(7 + rank)
-    feeds = []
+    batches = []
     for i in range(Ke + 2):
         idx = rng.randint(0, n_rows, B)
         xb = x[idx]
         keep = rng.rand(xb.nnz) >= w['corr_frac']
-        feeds.append(HostFeed(xb, xb.data * keep, labels[idx]))
+        batches.append((xb, xb.data * keep, labels[idx]))
+    cap = max(b[0].nnz for b in batches)   # one device layout for every feed -> the step is captured once and replayed
+    feeds = [HostFeed(xb, xc, lb, cap_nnz=None if args.no_graph else cap) for xb, xc, lb in batches]
     for f in feeds[:2]:
         eng.run_feed(f)
     if world > 1:

@@ -60,9 +60,14 @@ class HostFeed:
     """One step's inputs packed into ONE pinned host buffer (what `feed_dict` is to the reference's session.run,
     autoencoder/autoencoder.py:228): [indptr int64 | indices int32 | values f32 | corrupted values f32 | labels f32]."""
 
-    def __init__(self, x_batch, x_corr_values, labels):
+    def __init__(self, x_batch, x_corr_values, labels, cap_nnz=None):
+        """cap_nnz: lay the buffer out for up to cap_nnz stored entries, so that every feed of a run has the SAME device
+        layout and the step can be replayed from one captured CUDA graph."""
         m = canonical_csr(x_batch)
-        B, nnz = m.shape[0], int(m.nnz)
+        B, real_nnz = m.shape[0], int(m.nnz)
+        assert cap_nnz is None or cap_nnz >= real_nnz
+        self.cap_nnz = cap_nnz
+        nnz = real_nnz if cap_nnz is None else int(cap_nnz)   # layout size
         self.B, self.nnz, self.F = B, nnz, m.shape[1]
 
         def al(n):
@@ -76,10 +81,10 @@ class HostFeed:
         self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
         hb = self.host.numpy()
         hb[self.off_indptr:self.off_indptr + 8 * (B + 1)] = m.indptr.astype(np.int64).view(np.uint8)
-        hb[self.off_indices:self.off_indices + 4 * nnz] = m.indices.astype(np.int32).view(np.uint8)
-        hb[self.off_values:self.off_values + 4 * nnz] = m.data.astype(np.float32).view(np.uint8)
+        hb[self.off_indices:self.off_indices + 4 * real_nnz] = m.indices.astype(np.int32).view(np.uint8)
+        hb[self.off_values:self.off_values + 4 * real_nnz] = m.data.astype(np.float32).view(np.uint8)
         xc = m.data if x_corr_values is None else x_corr_values
-        hb[self.off_values_c:self.off_values_c + 4 * nnz] = np.asarray(xc, dtype=np.float32).view(np.uint8)
+        hb[self.off_values_c:self.off_values_c + 4 * real_nnz] = np.asarray(xc, dtype=np.float32).view(np.uint8)
         lab = np.zeros(B, np.float32) if labels is None else np.asarray(labels, dtype=np.float32).reshape(-1)
         hb[self.off_labels:self.off_labels + 4 * B] = lab.view(np.uint8)
         self.has_labels = labels is not None
@@ -140,6 +145,9 @@ class TrainEngine:
         self.launches = 0  # kernels launched by this engine (bench.py reports it)
         self.timed = None  # {kernel name: [(start_event, end_event), ...]} when per-kernel timing is on
         self._feed_dev = None
+        self._feed_graph = None
+        self._graph2 = None
+        self._ctl_owner = None
         self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
 
     # ---- kernel launch plumbing --------------------------------------------------------------------------------------
@@ -165,19 +173,36 @@ class TrainEngine:
 
     # ---- per-step host feed (the session.run(feed_dict) analog) ---------------------------------------------------------
     def run_feed(self, feed, stats_log_row=None):
-        """H2D copy of one packed pinned HostFeed, one training step on it, D2H read of the step's scalars."""
+        """H2D copy of one packed pinned HostFeed, one training step on it, D2H read of the step's scalars.
+        Feeds built with a common `cap_nnz` share one device layout: the step is then captured once and replayed."""
         if self._feed_dev is None or self._feed_dev.numel() < feed.nbytes:
             self._feed_dev = torch.empty(max(feed.nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+            self._feed_graph = None
         d = self._feed_dev
         d[:feed.nbytes].copy_(feed.host, non_blocking=True)
         B, nnz = feed.B, feed.nnz
-        v = lambda off, nb, dt: d[off:off + nb].view(dt)
-        csr = _CSRView(v(feed.off_indptr, 8 * (B + 1), torch.int64), v(feed.off_indices, 4 * nnz, torch.int32),
-                       v(feed.off_values, 4 * nnz, torch.float32), (B, feed.F))
-        self.csr = self.csr_c = csr
-        self.values_c = v(feed.off_values_c, 4 * nnz, torch.float32)
-        self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
-        self.step(None, 0, B, stats_log_row)
+        key = (B, nnz, feed.has_labels, feed.F)
+        fixed = feed.cap_nnz is not None and os.environ.get('DAE_CUDA_GRAPH', '1') == '1'
+        if not (fixed and self._feed_graph is not None and self._feed_graph[0] == key):
+            v = lambda off, nb, dt: d[off:off + nb].view(dt)
+            csr = _CSRView(v(feed.off_indptr, 8 * (B + 1), torch.int64), v(feed.off_indices, 4 * nnz, torch.int32),
+                           v(feed.off_values, 4 * nnz, torch.float32), (B, feed.F))
+            self.csr = self.csr_c = csr
+            self.values_c = v(feed.off_values_c, 4 * nnz, torch.float32)
+            self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
+            if fixed:   # capture the step on this layout (restores the parameters after its warm-up steps)
+                saved = (self._graph, self._graph2)
+                g = self.capture_step_graph(None, B, None, row_stride=0)
+                self._feed_graph = (key, g, self._graph2)
+                self._graph, self._graph2 = saved
+                self._ctl_owner = None
+        if fixed:
+            if self._ctl_owner != 'feed':   # cursors: offset 0 / log row 0 never move (stride 0); the optimizer step advances on the device
+                self.ctl.copy_(torch.tensor([0, 0, self.step_count + 1, 0], dtype=torch.int64))
+                self._ctl_owner = 'feed'
+            self._replay(self._feed_graph[1], self._feed_graph[2])
+        else:
+            self.step(None, 0, B, stats_log_row)
         self._stats_host.copy_(self.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         s = self._stats_host.numpy()
@@ -222,6 +247,7 @@ class TrainEngine:
         if B <= self._ws_B:
             return
         self._graph = None  # buffers move: a captured step graph (if any) is stale and must be re-captured
+        self._feed_graph = None
         f32 = dict(dtype=torch.float32, device=self.device)
         i32 = dict(dtype=torch.int32, device=self.device)
         self.E = torch.empty(B, self.H, **f32)
@@ -265,6 +291,7 @@ class TrainEngine:
         if cap > self._ent_cap:
             cap = int(cap * 1.5) if c.max_row_nnz is None else cap   # per-step host feeds vary in size: grow geometrically
             self._graph = None
+            self._feed_graph = None
             self.ent_col = torch.empty(cap, dtype=torch.int32, device=self.device)
             self.ent_row = torch.empty(cap, dtype=torch.int32, device=self.device)
             self.ent_val = torch.empty(cap, dtype=torch.float32, device=self.device)
@@ -570,13 +597,17 @@ class TrainEngine:
 
     def set_step_cursor(self, offset, log_row=0):
         """Host-side (re)positioning of the device cursors, e.g. at an epoch start."""
+        self._ctl_owner = 'fit'
         self.ctl.copy_(torch.tensor([int(offset), int(log_row), self.step_count + 1, 0], dtype=torch.int64), non_blocking=False)
 
     def replay_step(self):
-        self._graph.replay()
-        if self._graph2 is not None:
+        self._replay(self._graph, self._graph2)
+
+    def _replay(self, g, g2):
+        g.replay()
+        if g2 is not None:
             torch.distributed.all_reduce(self.grad, group=self.pg)
-            self._graph2.replay()
+            g2.replay()
         self.step_count += 1
         self.launches += self.graph_launches
 

@@ -269,3 +269,26 @@ def test_triplet_estimator_fit(gemm_mode):
     m1.fit(data)
     assert rel_err(m1.train_cost_batch[0][0], o['cost']) < REL_TOL
     assert rel_err(m1.train_cost_batch[2][0], o['triplet_loss']) < REL_TOL
+
+
+def test_host_feed_graph_replay_matches_eager(gemm_mode, monkeypatch):
+    """TrainEngine.run_feed (the session.run(feed_dict) analogue): feeds with a common cap_nnz are replayed from one captured
+    graph and give the same trajectory as eager per-feed launches."""
+    from dae_rnn_news_recommendation_b200.engine import HostFeed
+    F, H, B, steps = 400, 32, 64, 4
+    rng = np.random.default_rng(71)
+    W0 = xavier(F, H, 72) * 3
+    batches = []
+    for s in range(steps):
+        xb = random_csr(B, F, 12, seed=80 + s)
+        keep = rng.random(xb.nnz) >= 0.3
+        batches.append((xb, (xb.data * keep).astype(np.float32), rng.integers(0, 4, B).astype(np.float32)))
+    cap = max(b[0].nnz for b in batches)
+    res = []
+    for fixed in (False, True):
+        eng = _engine(F, H, opt='momentum', learning_rate=0.05, triplet_strategy='batch_all')
+        eng.set_parameters(W0)
+        costs = [eng.run_feed(HostFeed(xb, xc, lb, cap_nnz=cap if fixed else None))['cost'] for xb, xc, lb in batches]
+        res.append((costs, eng.get_parameters()['enc_w'], eng.step_count))
+    assert res[0][2] == res[1][2] == steps
+    assert rel_err(res[1][0], res[0][0]) < 1e-5 and rel_err(res[1][1], res[0][1]) < 1e-5
