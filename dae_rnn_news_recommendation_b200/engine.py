@@ -387,6 +387,17 @@ class TrainEngine:
             self._mining(B, strat, tc)
         self._decode_and_backward(B, self.rows, self.weight if strat != 0 else None, train)
         if fork:
+            # the step's scalars only need the decode row losses (main branch) and the mining statistics (side branch): reduce
+            # them on the side branch while the main one continues with the backward GEMM / encode backward / optimizer
+            ev3 = torch.cuda.Event()
+            ev3.record(torch.cuda.current_stream())
+            self._side.wait_event(ev3)
+            with torch.cuda.stream(self._side):
+                self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(self.weight), B, strat, self.alpha, ptr(self.stats),
+                        ptr(stats_log_row), ptr(ctl), _stream())
+                ev4 = torch.cuda.Event()
+                ev4.record(self._side)
+            self._finalize_done = True
             torch.cuda.current_stream().wait_event(ev2)
         if strat != 0 and train:  # dE += alpha (G + G^T) E
             if tc:
@@ -398,6 +409,8 @@ class TrainEngine:
                 self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
                 self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
         self._encode_backward_and_update(B, self.rows, self.weight if strat != 0 else None, strat, stats_log_row, train)
+        if fork:
+            torch.cuda.current_stream().wait_event(ev4)   # join before the cursors advance / the next step reuses `stats`
 
     def _mining(self, B, strat, tc):
         """S = E.E^T and the triplet kernel (loss, statistics, G = dL/dS; batch_hard: also the data weights)."""
@@ -483,8 +496,11 @@ class TrainEngine:
         elif train:
             self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
                     ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
-        self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(weight), B, strat,
-                self.alpha, ptr(self.stats), ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
+        if getattr(self, '_finalize_done', False):
+            self._finalize_done = False          # already issued on the side branch
+        else:
+            self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(weight), B, strat,
+                    self.alpha, ptr(self.stats), ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
         if not train or getattr(self, '_defer_update', False):
             return
         self._apply_update()
