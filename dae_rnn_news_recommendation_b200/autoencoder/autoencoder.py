@@ -209,6 +209,8 @@ class DenoisingAutoencoder(object):
             t0 = time.time()
             self._corrupt_on_device(host_csr, i)
             perm_buf.copy_(self._epoch_permutation(n))
+            if world > 1:   # every rank must slice the SAME permutation (also when the run is unseeded)
+                torch.distributed.broadcast(perm_buf, src=0, group=eng.pg)
             if use_graph:
                 if eng._graph is None:  # first epoch, or the workspaces were re-allocated (e.g. by a larger validation batch)
                     eng.capture_step_graph(perm_buf, bs, log, row_stride=bs * world)

@@ -82,6 +82,8 @@ class DenoisingAutoencoderTriplet(DenoisingAutoencoder):
                 xc = sp.vstack([utils.salt_and_pepper_noise(h, v) for h in host]).tocsr()
                 eng.set_data(csr, None, None, csr_corrupt=DeviceCSR(xc, eng.device))
             perm = self._epoch_permutation(n)
+            if world > 1:
+                torch.distributed.broadcast(perm, src=0, group=eng.pg)
             for k, s in enumerate(starts):
                 eng.step_explicit(perm, s, min(bs, n - s), n, log[k])
             torch.cuda.synchronize(eng.device)
