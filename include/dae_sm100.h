@@ -254,6 +254,21 @@ int dae_rownorm_split_bf16(const float* X, int32_t rows, int32_t cols, int64_t l
 int dae_row_argmax(float* S, int32_t rows, int32_t cols, int64_t ld, int64_t diag_offset, int32_t zero_diag,
                    int32_t* idx_out, float* val_out, void* stream);
 
+/* ---- "next" row: related-vs-unrelated AUROC of a pairwise similarity matrix ---------------------
+ * Replaces the numeric part of helpers.visualize_pairwise_similarity (helpers.py:88-100).
+ * dae_pair_partition: for every pair i > j of the strict lower triangle with labels[i] >= 0 and labels[j] >= 0
+ *   (-1 = missing, helpers.py:91) append S[i, j] to `related` if labels[i] == labels[j] (helpers.py:92-95) else to
+ *   `unrelated` (helpers.py:96-97).  cursors[0..1] are device counters the caller zeroes; on return they hold the
+ *   group sizes.  Order inside a group is unspecified.  Capacity: R = sum_c n_c(n_c-1)/2, U = M(M-1)/2 - R floats.
+ * dae_auroc_count: *twice_u += sum_q 2*#{t < q} + #{t == q} (query_is_positive = 1: queries are the related scores,
+ *   sorted_targets the ascending unrelated scores) or sum_q 2*#{t > q} + #{t == q} (0: roles swapped).  Then
+ *   AUROC = twice_u / (2 R U) -- the area sklearn's roc_curve + auc (helpers.py:99-100) return, ties included.
+ */
+int dae_pair_partition(const float* S, int64_t lds, int32_t n, const int32_t* labels, float* related, float* unrelated,
+                       uint64_t* cursors, void* stream);
+int dae_auroc_count(const float* queries, int64_t n_queries, const float* sorted_targets, int64_t n_targets,
+                    int32_t query_is_positive, uint64_t* twice_u, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,8 +6,10 @@
 
 Same flag names, defaults, asserts and `.env` override as the reference (python-dotenv; the two env typos at
 main_autoencoder.py:79-80 are fixed and `adam` is accepted).  Data preparation follows
-main_autoencoder.py:177-238 (CountVectorizer -> binary / tf-idf CSR, factorised labels); the similarity / plotting
-tail (:307-360, matplotlib + sklearn) is outside the accelerated path and is not reproduced.
+main_autoencoder.py:177-238 (CountVectorizer -> binary / tf-idf CSR, factorised labels).  The evaluation tail (:307-360) runs on
+the GPU as numbers, not pictures: pairwise similarity of the inputs and of the embeddings, related-vs-unrelated AUROC + box
+statistics (one JSON per reference plot file name under <plot_dir>) and the most-similar-article lookup; drawing with matplotlib
+is not reproduced.
 """
 import argparse
 import os
@@ -143,6 +145,35 @@ def prepare_synthetic(F):
     return X[:n - nv], X[n - nv:], lab[:n - nv], lab[n - nv:]
 
 
+def evaluate(F, model, trX, vlX, trL, vlL, enc, enc_v, max_rows=20000):
+    """Reference main_autoencoder.py:307-360: cosine similarity of the input space and of the embeddings, the related / unrelated
+    comparison for the label in use, and the nearest article of the first rows.  N x N lives on the GPU only; sets larger than
+    `max_rows` (the reference runs 8000 / 2000 rows) are skipped."""
+    from dae_rnn_news_recommendation_b200 import helpers
+    out = {}
+    print('calculate similarity')
+    in_metric = 'cosine' if F.input_format == 'binary' else 'linear kernel'   # tf-idf rows are already l2-normalised (:314)
+    in_name = 'binary_count' if F.input_format == 'binary' else 'tfidf'
+    suffix = '(Category)' if F.label == 'category_publish_name' else '(Story)'
+    for split, X, E, lab in (('', trX, enc, trL), ('_validate', vlX, enc_v, vlL)):
+        if X is None or X.shape[0] < 2 or X.shape[0] > max_rows:
+            print('similarity%s skipped: %s rows' % (split, None if X is None else X.shape[0]))
+            continue
+        for name, data, metric in ((in_name, X, in_metric), ('encoded', E, 'cosine')):
+            sim = helpers.pairwise_similarity(data, metric=metric, to_host=False)
+            key = 'similarity_boxplot_%s%s%s' % (name, split, suffix)
+            out[key] = helpers.visualize_pairwise_similarity(lab, sim, plot='boxplot', title=key, save_path=model.plot_dir + key + '.png')
+            print('%s: AUROC %.4f  related median %.4f  unrelated median %.4f' % (
+                key, out[key]['auroc'], out[key]['related'].get('median', float('nan')), out[key]['unrelated'].get('median', float('nan'))))
+            del sim
+        idx, score = helpers.nearest_neighbors(E, metric='cosine')
+        out['nearest' + split] = (idx, score)
+        for i in range(min(3, len(idx))):
+            print('article %d%s: most similar %d (cosine %.4f)' % (i, split, idx[i], score[i]))
+    print('calculate similarity done')
+    return out
+
+
 def main(argv=None):
     F = check_flags(apply_env_overrides(build_parser().parse_args(argv)))
     print(__file__ + ': Start')
@@ -168,6 +199,7 @@ def main(argv=None):
     if F.save_tsv:
         np.savetxt(model.tsv_dir + 'article_encoded.tsv', enc, delimiter='\t')
         np.savetxt(model.tsv_dir + 'article_encoded_validate.tsv', enc_v, delimiter='\t')
+    model.evaluation = evaluate(F, model, trX, vlX, trL, vlL, enc, enc_v)
     print(__file__ + ': End')
     return model
 

@@ -44,3 +44,9 @@ def test_cli_end_to_end_on_synthetic():
     assert os.path.exists(model.data_dir + 'article_encoded.npy') and os.path.exists(model.model_path + '.npz')
     assert os.path.exists(model.parameter_file)
     assert model.train_cost_batch[0][-1] < model.history[0][0, 0]
+    ev = model.evaluation   # the reference's evaluation tail (main_autoencoder.py:307-360) as numbers
+    for key in ('similarity_boxplot_binary_count(Category)', 'similarity_boxplot_encoded(Category)',
+                'similarity_boxplot_binary_count_validate(Category)', 'similarity_boxplot_encoded_validate(Category)'):
+        assert 0.0 <= ev[key]['auroc'] <= 1.0 and os.path.exists(model.plot_dir + key + '.json')
+    idx, score = ev['nearest']
+    assert idx.shape == (960,) and (idx != range(960)).all() and (score <= 1.0 + 1e-5).all()

@@ -43,3 +43,15 @@ def test_sparse_matches_sklearn_and_nearest_neighbors():
     np.fill_diagonal(sim, -np.inf)
     idx, val = nearest_neighbors(e, chunk=512)
     assert (idx == sim.argmax(1)).mean() > 0.999 and np.allclose(val, sim.max(1), atol=2e-5)
+
+
+def test_sparse_similarity_beyond_one_register_block():
+    """More rows than the encode kernel holds per output row (4096) and not a multiple of 4: the N x N product is assembled
+    from column blocks (UCI runs 8000 rows through this path, main_autoencoder.py:309)."""
+    from dae_rnn_news_recommendation_b200.helpers import pairwise_similarity
+    from helpers import random_csr
+    x = random_csr(4501, 1500, 25, kind='binary', seed=11)
+    want = pairwise.cosine_similarity(x)
+    np.fill_diagonal(want, 0)
+    got = pairwise_similarity(x, metric='cosine')
+    assert got.shape == (4501, 4501) and np.abs(got - want).max() < 1e-5
