@@ -15,6 +15,7 @@ import torch
 from . import _cabi
 from ._cabi import call
 from .engine import DeviceCSR
+from .io_formats import save_file, read_file  # noqa: F401  (reference helpers.py:138-264)
 
 _NORM = {'': 0, 'l1': 1, 'l2': 2, 'max': 3}
 

@@ -110,10 +110,18 @@ def check_flags(F):
     return F
 
 
-def prepare_uci(F):
-    """main_autoencoder.py:177-238 with pandas >= 2 fixes (sort by the article_id column, no DataFrame.append)."""
+_LABELS = ('category_publish_name', 'story')
+_TSV_LABEL_COLUMNS = ['label_story', 'label_category_publish_name', 'title', 'story', 'category_publish_name']
+
+
+def prepare_uci(F, model=None):
+    """main_autoencoder.py:177-244 with pandas >= 2 fixes (sort by the article_id column, no DataFrame.append): vectorise the
+    newest train_row + validate_row articles and, when a model is given, write the data_dir cache the reference writes
+    (same file names and formats) so that --restore_previous_data finds it."""
+    import joblib
     import pandas as pd
     from sklearn.feature_extraction.text import CountVectorizer, TfidfTransformer
+    from dae_rnn_news_recommendation_b200.io_formats import save_file
     df = pd.read_parquet(F.data_path)
     if 'article_id' in df.columns:
         df = df.set_index('article_id', drop=False)
@@ -124,16 +132,69 @@ def prepare_uci(F):
     n_tr, n_va = F.train_row, F.validate_row
     df = df.iloc[0:n_tr + n_va].sample(frac=1)
     df = df.sort_values('article_id') if 'article_id' in df.columns else df.sort_index()
-    cv = CountVectorizer(stop_words='english', min_df=F.min_df, max_df=F.max_df, max_features=F.max_features, binary=False)
+    def df_bound(v):   # sklearn >= 1.2 validates: a proportion is a float in [0, 1], a document count an int >= 1
+        return float(v) if v <= 1 else int(v)
+    cv = CountVectorizer(stop_words='english', min_df=df_bound(F.min_df), max_df=df_bound(F.max_df), max_features=F.max_features,
+                         binary=False)
     X = cv.fit_transform(df.main_content[0:n_tr])
     Xv = cv.transform(df.main_content[n_tr:n_tr + n_va])
     tf = TfidfTransformer()
     Xt, Xtv = tf.fit_transform(X), tf.transform(Xv)
-    X.data = np.ones(len(X.data), dtype=np.float32)
-    Xv.data = np.ones(len(Xv.data), dtype=np.float32)
-    lab = df['label_' + F.label]
-    data = {'binary': (X, Xv), 'tfidf': (Xt, Xtv)}[F.input_format]
-    return data[0].astype(np.float32), data[1].astype(np.float32), lab[0:n_tr].values, lab[n_tr:n_tr + n_va].values
+    d = {'articles': df.iloc[0:n_tr], 'articles_validate': df.iloc[n_tr:n_tr + n_va], 'tfidf': (Xt, Xtv),
+         'count_vectorizer': cv, 'tfidf_transformer': tf}
+    for lab in _LABELS:
+        d['label_' + lab] = (df['label_' + lab][0:n_tr], df['label_' + lab][n_tr:n_tr + n_va])
+    if model is not None:
+        dd = model.data_dir
+        save_file(d['articles'], dd + 'article.snappy.parquet')
+        save_file(d['articles_validate'], dd + 'article_validate.snappy.parquet')
+        for lab in _LABELS:
+            save_file(d['label_' + lab][0], dd + 'article_label_%s.pkl' % lab)
+            save_file(d['label_' + lab][1], dd + 'article_label_%s_validate.pkl' % lab)
+        save_file(X, dd + 'article_count_vectorized.npz')
+        save_file(Xv, dd + 'article_count_vectorized_validate.npz')
+    X.data = np.ones(len(X.data), dtype=X.data.dtype)      # binary bag of words (main_autoencoder.py:234-235)
+    Xv.data = np.ones(len(Xv.data), dtype=Xv.data.dtype)
+    d['binary'] = (X, Xv)
+    if model is not None:
+        save_file(X, dd + 'article_binary_count_vectorized.npz')
+        save_file(Xv, dd + 'article_binary_count_vectorized_validate.npz')
+        save_file(Xt, dd + 'article_tfidf_vectorized.npz')
+        save_file(Xtv, dd + 'article_tfidf_vectorized_validate.npz')
+        joblib.dump(cv, dd + 'count_vectorizer.joblib')
+        joblib.dump(tf, dd + 'tfidf_transformer.joblib')
+    return d
+
+
+def restore_uci(model):
+    """--restore_previous_data (main_autoencoder.py:161-175): read back the cache of an earlier run with the same model name."""
+    import joblib
+    from dae_rnn_news_recommendation_b200.io_formats import read_file
+    dd = model.data_dir
+    d = {'articles': read_file(dd + 'article.snappy.parquet'), 'articles_validate': read_file(dd + 'article_validate.snappy.parquet'),
+         'binary': (read_file(dd + 'article_binary_count_vectorized.npz'), read_file(dd + 'article_binary_count_vectorized_validate.npz')),
+         'tfidf': (read_file(dd + 'article_tfidf_vectorized.npz'), read_file(dd + 'article_tfidf_vectorized_validate.npz')),
+         'count_vectorizer': joblib.load(dd + 'count_vectorizer.joblib'), 'tfidf_transformer': joblib.load(dd + 'tfidf_transformer.joblib')}
+    for lab in _LABELS:
+        d['label_' + lab] = (read_file(dd + 'article_label_%s.pkl' % lab, data_type='pandas_series'),
+                             read_file(dd + 'article_label_%s_validate.pkl' % lab, data_type='pandas_series'))
+    return d
+
+
+def save_tsv(model, d, enc, enc_v):
+    """--save_tsv (main_autoencoder.py:292-301): the projector-ready TSV set under tsv_dir."""
+    from dae_rnn_news_recommendation_b200.io_formats import save_file
+    td = model.tsv_dir
+    if d is not None:
+        for name in ('tfidf', 'binary'):
+            stem = 'article_tfidf_vectorized' if name == 'tfidf' else 'article_binary_count_vectorized'
+            save_file(d[name][0], td + stem + '.tsv')
+            save_file(d[name][1], td + stem + '_validate.tsv')
+        cols = [c for c in _TSV_LABEL_COLUMNS if c in d['articles'].columns]
+        save_file(d['articles'][cols], td + 'article_label.tsv')
+        save_file(d['articles_validate'][cols], td + 'article_label_validate.tsv')
+    save_file(np.asarray(enc), td + 'article_encoded.tsv')
+    save_file(np.asarray(enc_v), td + 'article_encoded_validate.tsv')
 
 
 def prepare_synthetic(F):
@@ -184,7 +245,13 @@ def main(argv=None):
         loss_func=F.loss_func, main_dir=F.main_dir, opt=F.opt, learning_rate=F.learning_rate, momentum=F.momentum,
         verbose=F.verbose, verbose_step=F.verbose_step, num_epochs=F.num_epochs, batch_size=F.batch_size, alpha=F.alpha,
         triplet_strategy=F.triplet_strategy, rng_mode=F.rng_mode)
-    trX, vlX, trL, vlL = prepare_synthetic(F) if F.synthetic else prepare_uci(F)
+    data = None
+    if F.synthetic:
+        trX, vlX, trL, vlL = prepare_synthetic(F)
+    else:
+        data = restore_uci(model) if F.restore_previous_data else prepare_uci(F, model)
+        (trX, vlX), (trL, vlL) = data[F.input_format], data['label_' + F.label]
+        trX, vlX, trL, vlL = trX.astype(np.float32), vlX.astype(np.float32), np.asarray(trL), np.asarray(vlL)
     print('fit')
     model.fit(train_set=trX, validation_set=vlX if F.validation else None, train_set_label=trL,
               validation_set_label=vlL if F.validation else None, restore_previous_model=F.restore_previous_model)
@@ -197,8 +264,7 @@ def main(argv=None):
     enc_v = model.transform(utils.decay_noise(vlX, F.corr_frac), name='article_encoded_validate', save=F.encode_full)
     print('encoded: train %s validate %s (train_time of the last epoch: %.3f s)' % (enc.shape, enc_v.shape, model.train_time))
     if F.save_tsv:
-        np.savetxt(model.tsv_dir + 'article_encoded.tsv', enc, delimiter='\t')
-        np.savetxt(model.tsv_dir + 'article_encoded_validate.tsv', enc_v, delimiter='\t')
+        save_tsv(model, data, enc, enc_v)
     model.evaluation = evaluate(F, model, trX, vlX, trL, vlL, enc, enc_v)
     print(__file__ + ': End')
     return model

@@ -37,3 +37,19 @@ def mask_csr(m, frac, seed=1):
 def xavier(F, H, seed=0):
     b = np.sqrt(6.0 / (F + H))
     return np.random.default_rng(seed).uniform(-b, b, (F, H)).astype(np.float32)
+
+
+def load_uci_c1():
+    """BASELINE.json configs[0] data (tests/golden/uci_c1.npz, written by tools/make_uci_fixture.py from the UCI corpus with the
+    CLI's own preparation): binary CSR train 8000 x 10000 / validate 2000 x 10000, raw counts, category + story labels."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'uci_c1.npz'))
+    out = {}
+    for split in ('train', 'validate'):
+        shape = tuple(int(v) for v in z[split + '_shape'])
+        ind, ptr = z[split + '_indices'].astype(np.int32), z[split + '_indptr'].astype(np.int64)
+        out[split] = sp.csr_matrix((np.ones(len(ind), dtype=np.float32), ind, ptr), shape=shape)
+        out[split + '_counts'] = sp.csr_matrix((z[split + '_counts'].astype(np.float32), ind, ptr), shape=shape)
+        for lab in ('category_publish_name', 'story'):
+            out['%s_label_%s' % (split, lab)] = z['%s_label_%s' % (split, lab)]
+    return out
