@@ -7,6 +7,7 @@
 // chunks of 128 with masked (zero) entries compacted away, then every thread gathers its 128-bit slice of W[col,:]
 // with read-only vector loads, several rows of W in flight per thread.  W (20 MB at F=10k,H=500) is L2 resident,
 // so the gather runs at L2 bandwidth; HBM only sees the CSR stream, W once, and the E write.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -26,7 +27,8 @@ __device__ __forceinline__ void ldg_vec(const float* p, float (&out)[VW]) {
 
 constexpr int kEncThreads = 128;
 
-// stage up to 128 (col,val) pairs of the row into smem, dropping zeros; returns the number kept.
+// stage up to NT (= CTA size) (col,val) pairs of the row into smem, dropping zeros; returns the number kept.
+template <int NT = 128>
 __device__ __forceinline__ int stage_row_chunk(const int32_t* __restrict__ indices, const float* __restrict__ values,
                                                int64_t base, int64_t p1, float in_scale, int* s_col, float* s_val,
                                                int* s_wcnt) {
@@ -41,22 +43,29 @@ __device__ __forceinline__ int stage_row_chunk(const int32_t* __restrict__ indic
   __syncthreads();
   int off = 0, total = 0;
 #pragma unroll
-  for (int i = 0; i < kEncThreads / 32; ++i) { const int n = s_wcnt[i]; if (i < w) off += n; total += n; }
+  for (int i = 0; i < NT / 32; ++i) { const int n = s_wcnt[i]; if (i < w) off += n; total += n; }
   if (keep) { const int pos = off + __popc(m & ((1u << lane) - 1u)); s_col[pos] = c; s_val[pos] = v; }
   __syncthreads();
   return total;
 }
 
-template <int ACT, int VW, int NC>
-__global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
+// One CTA per row, G groups of 128 threads.  A group owns a full copy of the row's H accumulators and takes every G-th staged
+// entry, so a row has G x 8 W-row loads in flight: the kernel is bound by the LATENCY of the longest row of the batch (all rows
+// are resident at once), not by bandwidth -- real text has rows 10x the mean (UCI: mean 155 words, batch maximum ~1000).
+// The group partial sums are combined through shared memory and group 0 applies the epilogue.
+template <int ACT, int VW, int NC, int G>
+__global__ void __launch_bounds__(kEncThreads * G) encode_fwd_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
     const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ W, const float* __restrict__ bh,
     float* __restrict__ E, int64_t ldE, int32_t* __restrict__ col_count, __nv_bfloat16* __restrict__ e_hi,
     __nv_bfloat16* __restrict__ e_lo, int64_t ld_split) {
-  __shared__ int s_col[kEncThreads];
-  __shared__ float s_val[kEncThreads];
-  __shared__ int s_wcnt[kEncThreads / 32];
+  constexpr int NT = kEncThreads * G;
+  __shared__ int s_col[NT];
+  __shared__ float s_val[NT];
+  __shared__ int s_wcnt[NT / 32];
+  __shared__ float s_red[(G > 1 ? G - 1 : 1) * kEncThreads * VW];
   const int tid = threadIdx.x;
+  const int grp = tid / kEncThreads, gt = tid % kEncThreads;   // group, thread inside the group
   const int r = blockIdx.x;
   const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
   const int64_t p0 = indptr[row], p1 = indptr[row + 1];
@@ -65,16 +74,16 @@ __global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
   int hcol[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    hcol[c] = (tid + c * kEncThreads) * VW;
+    hcol[c] = (gt + c * kEncThreads) * VW;
 #pragma unroll
     for (int e = 0; e < VW; ++e) acc[c][e] = 0.0f;
   }
 
-  for (int64_t base = p0; base < p1; base += kEncThreads) {
-    const int total = stage_row_chunk(indices, values, base, p1, in_scale, s_col, s_val, s_wcnt);
+  for (int64_t base = p0; base < p1; base += NT) {
+    const int total = stage_row_chunk<NT>(indices, values, base, p1, in_scale, s_col, s_val, s_wcnt);
     if (col_count != nullptr && tid < total) atomicAdd(col_count + s_col[tid], 1);  // per-column entry counts for the backward gather
 #pragma unroll 8
-    for (int q = 0; q < total; ++q) {
+    for (int q = grp; q < total; q += G) {
       const float v = s_val[q];
       const float* wrow = W + (int64_t)s_col[q] * H;
 #pragma unroll
@@ -88,6 +97,25 @@ __global__ void __launch_bounds__(kEncThreads) encode_fwd_kernel(
       }
     }
     __syncthreads();
+  }
+  if constexpr (G > 1) {   // fixed summation order (group 0 + 1 + 2 + ...): results do not depend on scheduling
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (grp > 0) {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) s_red[((grp - 1) * kEncThreads + gt) * VW + e] = acc[c][e];
+      }
+      __syncthreads();
+      if (grp == 0) {
+#pragma unroll
+        for (int g = 1; g < G; ++g) {
+#pragma unroll
+          for (int e = 0; e < VW; ++e) acc[c][e] += s_red[((g - 1) * kEncThreads + gt) * VW + e];
+        }
+      }
+      __syncthreads();
+    }
+    if (grp != 0) return;
   }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -328,17 +356,30 @@ __global__ void __launch_bounds__(kEncThreads) encode_bwd_gather_kernel(const in
 }
 
 template <int ACT, int VW>
-static int launch_fwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
+static int launch_fwd_nc(int nc, int groups, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
                          const int32_t* rows, int H, float in_scale, const float* W, const float* bh, float* E, int64_t ldE,
                          int32_t* col_count, void* e_hi, void* e_lo, int64_t ld_split) {
-  switch (nc) {
-    case 1: encode_fwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
-    case 2: encode_fwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
-    case 4: encode_fwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
-    default: encode_fwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split); break;
+#define DAE_FWD(NC, G) encode_fwd_kernel<ACT, VW, NC, G><<<grid, kEncThreads * G, 0, st>>>(indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, \
+    col_count, (__nv_bfloat16*)e_hi, (__nv_bfloat16*)e_lo, ld_split)
+  if (groups == 4) {
+    switch (nc) {
+      case 1: DAE_FWD(1, 4); break;
+      case 2: DAE_FWD(2, 4); break;
+      case 4: DAE_FWD(4, 4); break;
+      default: DAE_FWD(8, 4); break;
+    }
+  } else {
+    switch (nc) {
+      case 1: DAE_FWD(1, 1); break;
+      case 2: DAE_FWD(2, 1); break;
+      case 4: DAE_FWD(4, 1); break;
+      default: DAE_FWD(8, 1); break;
+    }
   }
+#undef DAE_FWD
   return 0;
 }
+
 template <int ACT, int VW>
 static int launch_bwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
                          const int32_t* rows, int H, float in_scale, const float* E, const float* bh, float* dE, int64_t ldE,
@@ -383,10 +424,14 @@ extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices,
   cudaStream_t st = (cudaStream_t)stream;
   if (col_count) DAE_CUDA(cudaMemsetAsync(col_count, 0, sizeof(int32_t) * F, st));
   dim3 grid(n_rows);
+  // Few rows (a training batch): every row is resident at once and the launch lasts as long as its longest row -> split rows over
+  // 4 thread groups.  Many rows (transform): throughput-bound, one group per row keeps more rows in flight.
+  static const int forced = getenv("DAE_ENC_GROUPS") ? atoi(getenv("DAE_ENC_GROUPS")) : 0;
+  const int groups = forced ? forced : (n_rows <= 148 * 32 ? 4 : 1);
   DAE_DISPATCH_ACT(enc_act, ACT, {
-    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
-    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
-    else launch_fwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
+    if (vw == 4) launch_fwd_nc<ACT, 4>(nc, groups, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
+    else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, groups, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
+    else launch_fwd_nc<ACT, 1>(nc, groups, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
   });
   DAE_CHECK_LAUNCH("dae_encode_csr_fwd");
   return DAE_OK;
