@@ -255,10 +255,13 @@ def main():
     tags = ['gemm_decode_fwd', 'gemm_decode_dW', 'gemm_decode_dE', 'gemm_gram', 'gemm_dE_tri', 'dae_encode_csr_fwd',
             'dae_encode_csr_bwd', 'dae_decode_loss_bwd', 'dae_colsum', 'dae_triplet_batch_all', 'dae_triplet_batch_hard',
             'dae_batch_prepare', 'dae_step_finalize', 'dae_optimizer_step']
+    fork = eng.fork_branches
+    eng.fork_branches = False   # per-kernel times are taken with the step serialised on one stream (no overlap with the mining branch)
     eng.time_kernels(tags)
     run(3, W)
     prof = {k: float(np.sum(v)) / 3.0 for k, v in eng.kernel_times_ms().items() if v}
     eng.time_kernels(None)
+    eng.fork_branches = fork
     nnz_batch = x.nnz / n_rows * B
     nnz_c_batch = nnz_batch * (1.0 - w['corr_frac'])
     rooflined = {k: v for k, v in prof.items() if kernel_work(k, w, nnz_c_batch, nnz_batch)[0]}
@@ -292,7 +295,9 @@ def main():
     gpu_launches = eng.launches - launches0
     if use_graph:  # events cannot bracket nodes inside a graph: time the dominant kernel in 3 extra eager steps right after
         eng.time_kernels([dominant])
+        eng.fork_branches = False
         run(3, W + 3 + K)
+        eng.fork_branches = fork
     dom_ms = eng.kernel_times_ms()[dominant]
     eng.time_kernels(None)
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -17,7 +17,7 @@ d = load_uci_c1()
 tf = TfidfTransformer().fit(d['train_counts'])
 inputs = {'train': {'binary_count': (d['train'], 'cosine'), 'tfidf': (tf.transform(d['train_counts']).astype(np.float32), 'linear kernel')},
           'validate': {'binary_count': (d['validate'], 'cosine'), 'tfidf': (tf.transform(d['validate_counts']).astype(np.float32), 'linear kernel')}}
-res = {'config': 'C1 UCI news 8000x10000 binary, H=500, B=800, masking 0.3, CE, SGD 0.1, %d epochs' % epochs, 'fit': {}, 'auroc': {}}
+res = {'config': 'C1 UCI news 8000x10000 binary, H=500, B=800, masking 0.3, CE, SGD 0.1, %d epochs, rng_mode=%s' % (epochs, os.environ.get('DAE_RNG_MODE', 'device')), 'fit': {}, 'auroc': {}}
 
 
 def auroc_all(split, name, data, metric):
@@ -33,7 +33,8 @@ for split in ('train', 'validate'):
 for strategy in ('none', 'batch_all'):
     m = DenoisingAutoencoder(model_name='uci_' + strategy, main_dir='uci_' + strategy, compress_factor=20, enc_act_func='sigmoid',
                              dec_act_func='sigmoid', loss_func='cross_entropy', corr_type='masking', corr_frac=0.3, opt='gradient_descent',
-                             learning_rate=0.1, num_epochs=epochs, batch_size=0.1, alpha=1, triplet_strategy=strategy, seed=0, verbose=False)
+                             learning_rate=0.1, num_epochs=epochs, batch_size=0.1, alpha=1, triplet_strategy=strategy, seed=0, verbose=False,
+                             rng_mode=os.environ.get('DAE_RNG_MODE', 'device'))   # 'numpy' = the reference's host RNG stream (~6 ms/epoch of np.random)
     t0 = time.time()
     m.fit(d['train'], None, d['train_label_category_publish_name'])
     wall = time.time() - t0
