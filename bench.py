@@ -389,7 +389,7 @@ def main():
                           'inputs larger than L2: every step reads batch rows not touched since the previous epoch; dataset CSR '
                           '+ per-step state (W, Z, grad ~ 92 MB) exceed the 126 MB L2'),
                    'loss_first_last': [float(losses[0, 0]), float(losses[-1, 0])],
-                   'launch': 'cuda graph replay' if use_graph else 'eager'},
+                   'launch': 'cuda graph replay' if use_graph else 'eager', 'grad_exchange': eng.allreduce_mode},
         'clocks': clk,
         'e2e': {'value': e2e_val, 'unit': 'articles/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 128, 'steps': Ke,
                 'api': 'TrainEngine.run_feed(HostFeed) per step: pinned host batch -> H2D -> step -> D2H scalars, synchronised'},

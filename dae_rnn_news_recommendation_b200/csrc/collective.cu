@@ -1,0 +1,77 @@
+// Data-parallel gradient all-reduce over NVSwitch multicast memory ("one all-reduce of the flat [dW|dbh|dbv] buffer").
+//
+// Reference op replaced: none -- the reference is single-process; this is the exchange step the row-sharded training adds between
+// the gradient kernels and dae_optimizer_step.  The NCCL all-reduce (torch.distributed) is the default; this kernel is the
+// in-graph alternative (TrainEngine, DAE_ALLREDUCE=multimem): the gradient buffer lives in symmetric memory that every rank maps,
+// bound to one multicast address, and each rank reduces 1/P of it IN THE SWITCH and broadcasts the sums:
+//
+//   barrier (all ranks' gradients complete)  ->  multimem.ld_reduce.add.v4.f32 on my slice (the switch pulls the P copies and adds)
+//   ->  multimem.st.v4.f32 of the sums (the switch writes all P copies)  ->  barrier (all sums landed everywhere)
+//
+// Per GPU that is N(P-1)/P bytes out and in over NVLink, no staging buffer, no intermediate HBM round trip, and -- being an
+// ordinary kernel on the step's stream -- it is captured inside the step's CUDA graph (NCCL's launch has to stay outside).
+// Barriers are per CTA: CTA b of rank r raises flag[b][r] on every peer and waits for its own flag[b][0..P-1]; a flag is a 0/1 word
+// that the waiter resets, so no epoch counter has to be kept in step with graph replays.
+#include "common.cuh"
+
+namespace dae {
+
+__device__ __forceinline__ unsigned cas_release_sys(unsigned* addr, unsigned expect, unsigned value) {
+  unsigned old;
+  asm volatile("atom.release.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(expect), "r"(value) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned cas_acquire_sys(unsigned* addr, unsigned expect, unsigned value) {
+  unsigned old;
+  asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(expect), "r"(value) : "memory");
+  return old;
+}
+
+// flags[p] = base of rank p's flag words (peer-mapped); word index = (phase * n_blocks + block) * world + source rank
+__device__ __forceinline__ void peer_barrier(unsigned* const* flags, int rank, int world, int phase) {
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    const int64_t slot = ((int64_t)phase * gridDim.x + blockIdx.x) * world;
+    __threadfence_system();
+    unsigned* remote = flags[threadIdx.x] + slot + rank;          // "rank `rank`, CTA b has arrived" on peer threadIdx.x
+    while (cas_release_sys(remote, 0u, 1u) != 0u) {}
+    unsigned* mine = flags[rank] + slot + threadIdx.x;            // wait for peer threadIdx.x's CTA b, then re-arm the word
+    while (cas_acquire_sys(mine, 1u, 0u) != 1u) {}
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) allreduce_multimem_kernel(float* __restrict__ mc, unsigned* const* __restrict__ flags, int rank, int world,
+                                                                 int64_t n) {
+  peer_barrier(flags, rank, world, 0);
+  const int64_t n4 = n >> 2;                                 // whole float4 packets; the <= 3 trailing floats go to rank 0
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t lo = (int64_t)rank * per;
+  const int64_t hi = (lo + per < n4) ? lo + per : n4;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    float* p = mc + (i << 2);
+    float a, b, c, d;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  }
+  if (rank == 0 && blockIdx.x == 0 && (n4 << 2) + (int64_t)threadIdx.x < n) {
+    float* p = mc + (n4 << 2) + threadIdx.x;
+    float a;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(a) : "l"(p) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+  }
+  peer_barrier(flags, rank, world, 1);
+}
+
+}  // namespace dae
+
+extern "C" int dae_allreduce_multimem(float* multicast_grad, void* const* peer_flags, int32_t rank, int32_t world, int64_t n,
+                                      int32_t n_blocks, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(multicast_grad && peer_flags && world >= 2 && world <= 32 && rank >= 0 && rank < world && n > 0 && n_blocks > 0 && n_blocks <= 1024,
+              "dae_allreduce_multimem: bad arguments (world=%d rank=%d n=%lld blocks=%d)", world, rank, (long long)n, n_blocks);
+  DAE_REQUIRE((reinterpret_cast<uintptr_t>(multicast_grad) & 15) == 0, "dae_allreduce_multimem: the multicast buffer must be 16-byte aligned");
+  allreduce_multimem_kernel<<<n_blocks, 512, 0, (cudaStream_t)stream>>>(multicast_grad, (unsigned* const*)peer_flags, rank, world, n);
+  DAE_CHECK_LAUNCH("dae_allreduce_multimem");
+  return DAE_OK;
+}

@@ -149,6 +149,12 @@ class TrainEngine:
         self._graph2 = None
         self._ctl_owner = None
         self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
+        # gradient exchange of the data-parallel step: 'nccl' (default) or 'multimem' (in-switch reduction by dae_allreduce_multimem,
+        # captured inside the step's graph; needs NVSwitch multicast)
+        self.allreduce_mode = os.environ.get('DAE_ALLREDUCE', 'nccl') if self.world > 1 else 'none'
+        assert self.allreduce_mode in ('none', 'nccl', 'multimem')
+        if self.allreduce_mode == 'multimem':
+            self._setup_multimem()
 
     # ---- kernel launch plumbing --------------------------------------------------------------------------------------
     def time_kernels(self, names):
@@ -505,13 +511,39 @@ class TrainEngine:
             return
         self._apply_update()
 
+    def _setup_multimem(self, n_blocks=148):
+        """Move the gradient buffer into symmetric memory bound to a multicast address and create the peer-mapped flag words
+        of dae_allreduce_multimem.  Collective over the process group."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.pg if self.pg is not None else torch.distributed.group.WORLD
+        grad = symm.empty(self.n_params, dtype=torch.float32, device=self.device)
+        grad.zero_()
+        h_grad = symm.rendezvous(grad, group)
+        if not getattr(h_grad, 'has_multicast_support', False) or not h_grad.multicast_ptr:
+            raise _cabi.DaeError('DAE_ALLREDUCE=multimem: this process group has no NVSwitch multicast support')
+        flags = symm.empty(2 * n_blocks * self.world, dtype=torch.int32, device=self.device)
+        flags.zero_()
+        h_flags = symm.rendezvous(flags, group)
+        self.grad = grad
+        self._mm = {'grad': h_grad, 'flags': h_flags, 'flag_buf': flags, 'mc_ptr': int(h_grad.multicast_ptr),
+                    'flag_ptrs': int(h_flags.buffer_ptrs_dev), 'rank': int(h_grad.rank), 'blocks': int(n_blocks)}
+        torch.cuda.synchronize(self.device)
+        torch.distributed.barrier(group)   # every rank's flag words are zero before the first exchange
+
+    def _allreduce_grad(self):
+        if self.allreduce_mode == 'multimem':
+            m = self._mm
+            self._k('dae_allreduce_multimem', m['mc_ptr'], m['flag_ptrs'], m['rank'], self.world, self.n_params, m['blocks'], _stream())
+        else:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+
     def _apply_update(self, reduce=True):
         """Data parallel: ONE all-reduce of the flat [dW | dbh | dbv] buffer, then the fused optimizer (1/P folded in)."""
         F, H, st = self.F, self.H, _stream()
         gscale = 1.0
         if self.world > 1:
             if reduce:
-                torch.distributed.all_reduce(self.grad, group=self.pg)
+                self._allreduce_grad()
             gscale = 1.0 / self.world
         self.step_count += 1
         tc = self.gemm_mode == 'tc'
@@ -588,7 +620,7 @@ class TrainEngine:
         # up to the gradients and the step's scalars, eager all-reduce, graph 2 = optimizer + cursor advance).
         g = torch.cuda.CUDAGraph()
         g2 = None
-        if self.world == 1:
+        if self.world == 1 or self.allreduce_mode == 'multimem':   # the multimem exchange is a plain kernel: it is captured too
             with torch.cuda.graph(g):
                 self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
                 call('dae_step_advance', ptr(self.ctl), stride, _stream())

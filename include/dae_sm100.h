@@ -269,6 +269,19 @@ int dae_pair_partition(const float* S, int64_t lds, int32_t n, const int32_t* la
 int dae_auroc_count(const float* queries, int64_t n_queries, const float* sorted_targets, int64_t n_targets,
                     int32_t query_is_positive, uint64_t* twice_u, void* stream);
 
+/* ---- data-parallel exchange step: in-switch all-reduce of the flat gradient buffer -------------------
+ * The reference is single-process; row-sharded training adds ONE sum over ranks of [dW | dbh | dbv] between the
+ * gradient kernels and dae_optimizer_step.  Default transport: ncclAllReduce.  dae_allreduce_multimem is the
+ * in-graph alternative: `multicast_grad` is the NVSwitch multicast address bound to every rank's gradient buffer
+ * (symmetric memory, identical offset on every rank, n floats, 16-byte aligned); `peer_flags` is a DEVICE array of
+ * `world` pointers to each rank's flag words (2 * n_blocks * world zero-initialised uint32, peer-mapped).  Every
+ * rank calls it with the same n and n_blocks on its step stream; on return (stream order) every rank's buffer
+ * holds the sum.  Rank r reduces float4 packets [r*ceil(n4/P), ...) with multimem.ld_reduce and writes them back
+ * with multimem.st; CTA-level flag barriers open and close the exchange.
+ */
+int dae_allreduce_multimem(float* multicast_grad, void* const* peer_flags, int32_t rank, int32_t world, int64_t n,
+                           int32_t n_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
