@@ -27,6 +27,15 @@ __device__ __forceinline__ unsigned cas_acquire_sys(unsigned* addr, unsigned exp
   return old;
 }
 
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// A peer that never arrives (crashed rank, mismatched launch) must not leave this GPU spinning forever: after 5 s the kernel traps
+// and the error surfaces on the host at the next synchronisation.
+constexpr unsigned long long kBarrierTimeoutNs = 5000000000ull;
+
 // flags[p] = base of rank p's flag words (peer-mapped); word index = (phase * n_blocks + block) * world + source rank
 __device__ __forceinline__ void peer_barrier(unsigned* const* flags, int rank, int world, int phase) {
   __syncthreads();
@@ -34,9 +43,10 @@ __device__ __forceinline__ void peer_barrier(unsigned* const* flags, int rank, i
     const int64_t slot = ((int64_t)phase * gridDim.x + blockIdx.x) * world;
     __threadfence_system();
     unsigned* remote = flags[threadIdx.x] + slot + rank;          // "rank `rank`, CTA b has arrived" on peer threadIdx.x
-    while (cas_release_sys(remote, 0u, 1u) != 0u) {}
+    const unsigned long long t0 = now_ns();
+    while (cas_release_sys(remote, 0u, 1u) != 0u) { if (now_ns() - t0 > kBarrierTimeoutNs) __trap(); }
     unsigned* mine = flags[rank] + slot + threadIdx.x;            // wait for peer threadIdx.x's CTA b, then re-arm the word
-    while (cas_acquire_sys(mine, 1u, 0u) != 1u) {}
+    while (cas_acquire_sys(mine, 1u, 0u) != 1u) { if (now_ns() - t0 > kBarrierTimeoutNs) __trap(); }
   }
   __syncthreads();
 }
