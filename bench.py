@@ -1,21 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- articles/sec of the DAE-with-triplet-loss training hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--config C1|C2|C3|C4|C5] [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one training step (corrupt-> encode -> decode -> loss -> triplet mining -> backward -> optimizer) on one batch of
-B=800 synthetic articles of BASELINE.json configs[1]: 100k articles (or as many as the run consumes), 10 000-dim sparse
-TF-IDF (1 % nnz), 500 hidden units, batch_all triplet loss, sigmoid/sigmoid, cross-entropy, SGD.
-N>1: one process per GPU under torchrun (weak scaling: every rank trains B rows per step on its own shard, ONE NCCL
-all-reduce of the flat gradient per step).
+A "step" is one training step (corrupt -> encode -> decode -> loss -> triplet mining -> backward -> optimizer) on one batch of
+B = 800 articles.  Default workload = BASELINE.json configs[1] (C2): 100 000 synthetic articles per rank, 10 000-dim sparse TF-IDF
+(1 % nnz), 500 hidden units, batch_all triplet loss, sigmoid/sigmoid, cross-entropy, SGD.  The other configs of BASELINE.json are
+selectable (`--config`); their lines are committed under profiles/.
+N > 1: one process per GPU under torchrun (weak scaling: every rank trains B rows per step on its own shard, ONE exchange of the
+flat gradient per step).
 
-`--impl reference` times the reference algorithm restated on PyTorch-CPU (oracle/dae_oracle.py; TensorFlow 1.12 cannot
-be installed offline) on the host cores, same config.
+`--impl reference` times the reference algorithm restated on PyTorch-CPU (oracle/dae_oracle.py; TensorFlow 1.12 cannot be installed
+offline) on the host cores, same config.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -25,9 +25,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name='C2: synthetic tf-idf 10000-dim 1% nnz, H=500, batch_all, B=800', F=10000, H=500, B=800,
-                mean_nnz=100, kind='tfidf', n_classes=4, strategy='batch_all', loss='cross_entropy', enc='sigmoid',
-                dec='sigmoid', opt='gradient_descent', lr=0.1, corr_frac=0.3, alpha=1.0)
+_COMMON = dict(F=10000, H=500, B=800, mean_nnz=100, n_classes=4, loss='cross_entropy', enc='sigmoid', dec='sigmoid',
+               opt='gradient_descent', lr=0.1, corr_frac=0.3, alpha=1.0, rows=100000)
+CONFIGS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case, real data (fixture written by tools/make_uci_fixture.py)
+    'C1': dict(_COMMON, name='C1: UCI news 8000 x 10000 binary, H=500, triplet_strategy none, SGD, B=800', kind='uci', strategy='none',
+               rows=8000),
+    'C2': dict(_COMMON, name='C2: synthetic tf-idf 10000-dim 1% nnz, H=500, batch_all, B=800', kind='tfidf', strategy='batch_all'),
+    # 1M articles over 8 ranks = 125 000 rows per rank (what one rank of the 8-GPU job holds)
+    'C3': dict(_COMMON, name='C3: synthetic binary 10000-dim 1% nnz, masking 0.3, H=500, batch_hard, B=800 per rank', kind='binary',
+               strategy='batch_hard', rows=125000),
+    'C4': dict(_COMMON, name='C4: synthetic tf-idf 50000-dim 0.2% nnz, H=1000, batch_all, B=800 (CSR-SpMM stress)', kind='tfidf',
+               strategy='batch_all', F=50000, H=1000),
+    # 200k (anchor, pos, neg) triples over 4 ranks = 50 000 per rank; a step encodes/decodes 3 x 800 rows
+    'C5': dict(_COMMON, name='C5: explicit (anchor,pos,neg) triplets, binary 10000-dim 1% nnz, H=500, alpha=1, B=800 triples per rank',
+               kind='binary', strategy='explicit', rows=50000),
+}
 
 
 def parse():
@@ -36,17 +49,32 @@ def parse():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--rows', type=int, default=0, help='synthetic articles per rank (default: what the run consumes, <= 100k)')
-    ap.add_argument('--flush-l2', action='store_true', help='write a 256 MB buffer between timed steps (per-step events)')
+    ap.add_argument('--config', default='C2', choices=sorted(CONFIGS))
+    ap.add_argument('--rows', type=int, default=0, help='articles per rank (default: the config\'s count)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying the captured CUDA graph')
     ap.add_argument('--cpu-steps', type=int, default=3)
     return ap.parse_args()
 
 
-def make_data(n_rows, seed):
-    from dae_rnn_news_recommendation_b200.synth import make_sparse, make_labels
-    w = WORKLOAD
+def make_data(w, n_rows, seed):
+    """-> (x, labels) or, for the explicit-triplet config, ({'org','pos','neg'}, None)."""
+    from dae_rnn_news_recommendation_b200.synth import make_sparse, make_labels, perturb_rows
+    if w['kind'] == 'uci':
+        z = np.load(os.path.join(ROOT, 'tests', 'golden', 'uci_c1.npz'))
+        import scipy.sparse as sp
+        shape = tuple(int(v) for v in z['train_shape'])
+        ind, ptr = z['train_indices'].astype(np.int32), z['train_indptr'].astype(np.int64)
+        x = sp.csr_matrix((np.ones(len(ind), dtype=np.float32), ind, ptr), shape=shape)
+        reps = -(-n_rows // shape[0])
+        if reps > 1:
+            x = sp.vstack([x] * reps).tocsr()
+        return x[:n_rows], np.zeros(n_rows, np.float32)
+    if w['strategy'] == 'explicit':
+        org = make_sparse(n_rows, w['F'], w['mean_nnz'], 'binary', seed=seed)
+        pos = perturb_rows(org, 0.3, seed=seed + 1)
+        neg = make_sparse(n_rows, w['F'], w['mean_nnz'], 'binary', seed=seed + 2)
+        return {'org': org, 'pos': pos, 'neg': neg}, None
     x = make_sparse(n_rows, w['F'], w['mean_nnz'], w['kind'], seed=seed)
     return x, make_labels(n_rows, w['n_classes'], seed=seed)
 
@@ -59,24 +87,27 @@ def xavier(F, H, seed=0):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (reference algorithm on PyTorch-CPU), used for cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_steps(x, labels, n_steps, n_warm, seed=0):
+def cpu_steps(w, x, labels, n_steps, n_warm, seed=0):
     import torch
     from oracle.dae_oracle import OracleDAE, masking_noise
-    w = WORKLOAD
     torch.set_num_threads(os.cpu_count())
     B = w['B']
+    explicit = w['strategy'] == 'explicit'
     model = OracleDAE(xavier(w['F'], w['H'], seed), enc_act_func=w['enc'], dec_act_func=w['dec'], loss_func=w['loss'],
-                      opt=w['opt'], learning_rate=w['lr'], alpha=w['alpha'], triplet_strategy=w['strategy'])
+                      opt=w['opt'], learning_rate=w['lr'], alpha=w['alpha'],
+                      triplet_strategy='none' if explicit else w['strategy'])
     rng = np.random.RandomState(seed)
-    need = (n_steps + n_warm) * B
-    assert x.shape[0] >= need, (x.shape, need)
     times = []
     for s in range(n_steps + n_warm):
         t0 = time.perf_counter()
         sl = slice(s * B, (s + 1) * B)
-        xb = x[sl]
-        xc = masking_noise(xb, w['corr_frac'], rng)       # host corruption + batching are inside the reference's window
-        model.step(xb, xc, labels[sl])
+        if explicit:
+            xs = [x[k][sl] for k in ('org', 'pos', 'neg')]
+            model.step_explicit(xs, [masking_noise(m, w['corr_frac'], rng) for m in xs])
+        else:
+            xb = x[sl]
+            xc = masking_noise(xb, w['corr_frac'], rng)       # host corruption + batching are inside the reference's window
+            model.step(xb, xc, labels[sl])
         if s >= n_warm:
             times.append(time.perf_counter() - t0)
     return times
@@ -99,20 +130,20 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
-    w = WORKLOAD
+    w = CONFIGS[args.config]
     B = w['B']
-    warm = min(args.warmup, 1)
-    x, labels = make_data((warm + 1) * B, seed=0)
-    t_probe = cpu_steps(x, labels, 1, warm)[0]
+    warm = 1
+    x, labels = make_data(w, (warm + 1) * B, seed=0)
+    t_probe = cpu_steps(w, x, labels, 1, warm)[0]
     budget = 150.0
     k = int(max(1, min(args.steps, budget // max(t_probe, 1e-3))))
-    x, labels = make_data((k + 1) * B, seed=1)
-    times = cpu_steps(x, labels, k, 1)
+    x, labels = make_data(w, (k + 1) * B, seed=1)
+    times = cpu_steps(w, x, labels, k, 1)
     t = float(np.sum(times))
     val = k * B / t
     out = {'impl': 'reference', 'metric': 'articles/sec', 'value': val, 'unit': 'articles/s', 'n_gpus': args.gpus, 'steps': k,
            'steps_requested': args.steps, 'warmup': 1, 'ms_per_step': 1e3 * t / k, 'higher_is_better': True,
-           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'real (UCI news fixture)' if w['kind'] == 'uci' else 'synthetic',
            'config': {'workload': w['name'], 'global_batch': B, 'note': 'reference algorithm restated on PyTorch-CPU '
                       '(TF 1.12 unavailable offline); steps capped to fit ~150 s'},
            'cpu_baseline': {'value': val, 'unit': 'articles/s', 'cores': os.cpu_count(), 'kind': 'port',
@@ -122,73 +153,106 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# clocks sampler
+# clocks sampler: NVML polled from a thread (nvidia-smi's loop mode block-buffers its pipe and starts too slowly for a
+# timed region of a few milliseconds)
 # ----------------------------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, index):
-        self.lines = []
-        self.proc = None
-        self.index = index
+        self.index, self.samples, self.stop_flag, self.thr, self.h, self.err = index, [], False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._pump, daemon=True)
-            self.thr.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thr = threading.Thread(target=self._poll, daemon=True)
+        self.thr.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:   # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.time(), sm, rs))
+            except Exception as e:   # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.0005)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        sel = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
-        for l in sel:
-            f = [v.strip() for v in l.split(',')]
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(np.max(mx)) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        self.stop_flag = True
+        if self.thr is not None:
+            self.thr.join(timeout=2.0)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples: %s' % self.err], 'samples': 0}
+        sel = [s for s in self.samples if t0 <= s[0] <= t1]
+        inside = len(sel)
+        if not sel:   # the timed region was shorter than one NVML poll: take the samples around it
+            sel = [s for s in self.samples if t0 - 0.05 <= s[0] <= t1 + 0.05] or self.samples
+        reasons = set()
+        for _, _, rs in sel:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median([s[1] for s in sel])), 'sm_max_mhz': self.max_sm, 'reasons': sorted(reasons),
+                'samples': len(sel), 'samples_inside_timed_region': inside, 'source': 'NVML polled every ~0.5 ms'}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# roofline bookkeeping: algorithmic work per launch of each kernel tag
+# roofline bookkeeping: ALGORITHMIC work per launch of each kernel tag
 # ----------------------------------------------------------------------------------------------------------------------
-def kernel_work(tag, w, nnz_c_batch, nnz_batch):
-    B, F, H = w['B'], w['F'], w['H']
+def kernel_work(tag, w, s):
+    """-> (bound, work per launch).  s: measured batch statistics (nnz per batch, kept nnz, distinct columns, valid triplets)."""
+    F, H = w['F'], w['H']
+    B = w['B'] * (3 if w['strategy'] == 'explicit' else 1)      # rows through the encode / decode kernels per step
+    Hp = (H + 1 + 63) // 64 * 64
     if tag in ('gemm_decode_fwd', 'gemm_decode_dW', 'gemm_decode_dE'):
         return 'tensor', 2.0 * B * F * H
-    if tag == 'gemm_gram':
+    if tag in ('gemm_gram', 'gemm_dE_tri'):
         return 'tensor', 2.0 * B * B * H
-    if tag == 'gemm_dE_tri':
-        return 'tensor', 2.0 * B * B * H
-    if tag == 'dae_encode_csr_fwd':
-        return 'hbm', nnz_c_batch * 8.0 + (B + 1) * 8.0 + F * H * 4.0 + H * 4.0 + B * H * 4.0
-    if tag == 'dae_encode_csr_bwd':
-        return 'hbm', nnz_c_batch * (8.0 + H * 4.0 * 2.0)
-    if tag == 'dae_decode_loss_bwd':
-        return 'hbm', 2.0 * B * F * 4.0 + nnz_batch * 8.0
-    if tag == 'dae_colsum':
-        return 'hbm', B * F * 4.0
-    if tag == 'dae_optimizer_step':
-        return 'hbm', 3.0 * (F * H + F + H) * 4.0
+    if tag == 'dae_encode_csr_fwd':     # CSR stream (all stored entries are read), touched W rows once, E + its bf16 hi/lo copy out
+        return 'hbm', s['nnz'] * 8.0 + (B + 1) * 8.0 + s['cols'] * H * 4.0 + H * 4.0 + B * H * 4.0 + B * Hp * 4.0
+    if tag == 'dae_encode_csr_bwd':     # CSR stream, dE in / dA out once, bucketed entries out + in, touched dW rows read-modify-write
+        return 'hbm', s['nnz'] * 8.0 + 2.0 * B * H * 4.0 + s['nnz_c'] * 24.0 + s['cols_c'] * H * 8.0
+    if tag == 'dae_optimizer_step':     # theta, grad in; theta + bf16 hi/lo of W out
+        return 'hbm', 3.0 * (F * H + F + H) * 4.0 + F * Hp * 4.0
+    if tag == 'dae_triplet_batch_all':
+        return 'issue', s['triplets']
+    if tag == 'dae_triplet_batch_hard':
+        return 'hbm', 3.0 * B * B * 4.0
     return None, 0.0
+
+
+def batch_stats(w, x, labels, rng):
+    """Per-batch figures of the algorithmic-work model, measured on one host-side sample batch."""
+    B = w['B']
+    if w['strategy'] == 'explicit':
+        xb = [x[k][:B] for k in ('org', 'pos', 'neg')]
+        nnz = sum(m.nnz for m in xb)
+        idx = np.concatenate([m.indices for m in xb])
+    else:
+        xb = x[:B]
+        nnz, idx = xb.nnz, xb.indices
+    keep = rng.random(len(idx)) >= w['corr_frac']
+    s = {'nnz': float(nnz), 'nnz_c': float(keep.sum()), 'cols': float(len(np.unique(idx))), 'cols_c': float(len(np.unique(idx[keep]))),
+         'triplets': 0.0}
+    if w['strategy'] == 'batch_all':
+        _, cnt = np.unique(labels[:B], return_counts=True)
+        s['triplets'] = float(np.sum(cnt * (cnt - 1.0) * (B - cnt)))
+    return s
 
 
 def main():
@@ -199,7 +263,8 @@ def main():
     import torch
     import torch.distributed as dist
     from dae_rnn_news_recommendation_b200.engine import TrainEngine, DeviceCSR, HostFeed
-    w = WORKLOAD
+    import scipy.sparse as sp
+    w = CONFIGS[args.config]
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -208,17 +273,21 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     B, F, H, K, W = w['B'], w['F'], w['H'], args.steps, max(args.warmup, 3)
-    n_rows = args.rows or min(100000, (K + W + 8) * B)
-    n_rows = max(n_rows, (K + W) * B if (K + W) * B <= 100000 else 100000)
-    x, labels = make_data(n_rows, seed=1000 + rank)
+    explicit = w['strategy'] == 'explicit'
+    n_rows = args.rows or w['rows']
+    x, labels = make_data(w, n_rows, seed=1000 + rank)
+    stats = batch_stats(w, x, labels, np.random.default_rng(5))
 
     eng = TrainEngine(F, H, enc_act_func=w['enc'], dec_act_func=w['dec'], loss_func=w['loss'], opt=w['opt'],
                       learning_rate=w['lr'], alpha=w['alpha'], triplet_strategy=w['strategy'], device=dev)
     eng.set_parameters(xavier(F, H, 0))
-    csr = DeviceCSR(x, dev)
-    eng.set_data(csr, None, torch.from_numpy(labels).to(dev))
+    if explicit:
+        csr = DeviceCSR(sp.vstack([x['org'], x['pos'], x['neg']]).tocsr(), dev)
+        eng.set_data(csr, None, None)
+    else:
+        csr = DeviceCSR(x, dev)
+        eng.set_data(csr, None, torch.from_numpy(labels).to(dev))
     steps_per_epoch = n_rows // B
-
     perm_buf = torch.zeros(n_rows, dtype=torch.int32, device=dev)
     use_graph = not args.no_graph
 
@@ -226,10 +295,16 @@ def main():
         eng.corrupt_masking(w['corr_frac'], seed=1234 + rank, epoch=epoch)           # utils.masking_noise, on device
         perm_buf.copy_(torch.randperm(n_rows, device=dev, dtype=torch.int32))         # utils.gen_batches shuffle
 
+    def eager_step(offset, log_row):
+        if explicit:
+            eng.step_explicit(perm_buf, offset, B, n_rows, log_row)
+        else:
+            eng.step(perm_buf, offset, B, log_row)
+
     state = {'epoch': -1}
 
-    def run(n, first_step, log=None, flush=None, evs=None, graph=False):
-        """n steps starting at global step `first_step` (epoch boundaries re-corrupt + re-shuffle inside the window)."""
+    def run(n, first_step, log=None, graph=False):
+        """n steps starting at global step `first_step`; epoch boundaries re-corrupt + re-shuffle inside the window."""
         for i in range(n):
             ep, in_epoch = divmod(first_step + i, steps_per_epoch)
             if ep != state['epoch']:
@@ -237,87 +312,76 @@ def main():
                 state['epoch'] = ep
             if graph and (i == 0 or in_epoch == 0):
                 eng.set_step_cursor(in_epoch * B, i)
-            if flush is not None:
-                flush.add_(1.0)
-            if evs is not None:
-                evs[i][0].record()
             if graph:
                 eng.replay_step()
             else:
-                eng.step(perm_buf, in_epoch * B, B, None if log is None else log[i])
-            if evs is not None:
-                evs[i][1].record()
+                eager_step(in_epoch * B, None if log is None else log[i])
 
     run(W, 0)  # warm-up (also allocates the workspaces)
     torch.cuda.synchronize()
 
-    # -- per-kernel profile pass (3 steps, every kernel bracketed) to find the dominant kernel
+    # -- per-kernel pass: every kernel bracketed by CUDA events, the step serialised on ONE stream (no branch overlap), and the
+    #    stream PRE-LOADED behind a spin kernel so that the host's launch latency (tensor-map encodes, 8 ranks sharing the cores)
+    #    cannot sit between an event pair: the durations are device time only and do not depend on the rank count.
     tags = ['gemm_decode_fwd', 'gemm_decode_dW', 'gemm_decode_dE', 'gemm_gram', 'gemm_dE_tri', 'dae_encode_csr_fwd',
-            'dae_encode_csr_bwd', 'dae_decode_loss_bwd', 'dae_colsum', 'dae_triplet_batch_all', 'dae_triplet_batch_hard',
-            'dae_batch_prepare', 'dae_step_finalize', 'dae_optimizer_step']
-    fork = eng.fork_branches
-    eng.fork_branches = False   # per-kernel times are taken with the step serialised on one stream (no overlap with the mining branch)
-    eng.time_kernels(tags)
-    run(3, W)
-    prof = {k: float(np.sum(v)) / 3.0 for k, v in eng.kernel_times_ms().items() if v}
-    eng.time_kernels(None)
-    eng.fork_branches = fork
-    nnz_batch = x.nnz / n_rows * B
-    nnz_c_batch = nnz_batch * (1.0 - w['corr_frac'])
-    rooflined = {k: v for k, v in prof.items() if kernel_work(k, w, nnz_c_batch, nnz_batch)[0]}
-    dominant = max(rooflined, key=rooflined.get)
+            'dae_encode_csr_bwd', 'dae_triplet_batch_all', 'dae_triplet_batch_hard', 'dae_triplet_explicit',
+            'dae_batch_prepare', 'dae_batch_prepare_explicit', 'dae_step_finalize', 'dae_optimizer_step']
 
-    # -- timed region: EXACTLY K steps, barrier + synchronize on both sides, CUDA events, max over ranks
+    def profile(first_step, n=3):
+        fork = eng.fork_branches
+        eng.fork_branches = False
+        eng.time_kernels(tags)
+        torch.cuda.synchronize()
+        torch.cuda._sleep(60_000_000)          # ~30 ms of device spin: the n steps below are fully enqueued before they start
+        run(n, first_step)
+        out = {k: float(np.sum(v)) / n for k, v in eng.kernel_times_ms().items() if v}
+        eng.time_kernels(None)
+        eng.fork_branches = fork
+        return out
+
+    # -- timed region: EXACTLY K steps, barrier + synchronize on both sides, CUDA events, max over ranks.  The window starts at an
+    #    epoch boundary, so ONE corruption pass over the rank's whole set and ONE permutation are inside it.
+    first = -(-(W) // steps_per_epoch) * steps_per_epoch
     log = torch.zeros(K, 16, dtype=torch.float64, device=dev)
     if use_graph:
-        eng.capture_step_graph(perm_buf, B, log)   # one CUDA graph of the whole step; cursors live in device memory
-    flush = torch.zeros(64 * 1024 * 1024, device=dev) if args.flush_l2 else None
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)] if args.flush_l2 else None
-    eng.time_kernels(None if use_graph else [dominant])
+        eng.capture_step_graph(perm_buf, B, log, explicit_n=n_rows if explicit else None)   # one CUDA graph of the whole step
     launches0 = eng.launches
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    run(K, W + 3, log=log, flush=flush, evs=evs, graph=use_graph)
+    run(K, first, log=log, graph=use_graph)
     e1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1) if evs is None else float(sum(a.elapsed_time(b) for a, b in evs))
+    ms = e0.elapsed_time(e1)
     gpu_launches = eng.launches - launches0
-    if use_graph:  # events cannot bracket nodes inside a graph: time the dominant kernel in 3 extra eager steps right after
-        eng.time_kernels([dominant])
-        eng.fork_branches = False
-        run(3, W + 3 + K)
-        eng.fork_branches = fork
-    dom_ms = eng.kernel_times_ms()[dominant]
-    eng.time_kernels(None)
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
-    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     value = K * B * world / (ms * 1e-3)
     losses = log.cpu().numpy()
+    prof = profile(first + K)
 
     # -- e2e: per-step HOST feed (pinned) -> H2D -> step -> D2H of the step's scalars, through TrainEngine.run_feed
-    from dae_rnn_news_recommendation_b200.autoencoder import utils as hostutils
     Ke = min(K, 20)
     rng = np.random.RandomState(7 + rank)
     batches = []
     for i in range(Ke + 2):
         idx = rng.randint(0, n_rows, B)
-        xb = x[idx]
+        xb = sp.vstack([x[k][idx] for k in ('org', 'pos', 'neg')]).tocsr() if explicit else x[idx]
         keep = rng.rand(xb.nnz) >= w['corr_frac']
-        batches.append((xb, xb.data * keep, labels[idx]))
+        batches.append((xb, xb.data * keep, None if explicit else labels[idx]))
     cap = max(b[0].nnz for b in batches)   # one device layout for every feed -> the step is captured once and replayed
     feeds = [HostFeed(xb, xc, lb, cap_nnz=None if args.no_graph else cap) for xb, xc, lb in batches]
     for f in feeds[:2]:
@@ -337,34 +401,44 @@ def main():
     e2e_val = Ke * B * world / (float(tme.item()) * 1e-3)
     h2d = int(np.mean([f.nbytes for f in feeds[2:]]))
 
-    # -- roofline of the dominant kernel
+    # -- roofline table (every kernel of the step) and the longest kernel's entry
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except (OSError, ValueError):
         pass
-    bound, work = kernel_work(dominant, w, nnz_c_batch, nnz_batch)
-    dur = float(np.mean(dom_ms)) * 1e-3
-    if bound == 'tensor':
-        achieved, unit = work / dur / 1e12, 'TFLOP/s'
-        peak = peaks.get('bf16_tflops_sustained', 1400.0)
-        peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained'
-    else:
-        achieved, unit = work / dur / 1e9, 'GB/s'
-        peak = peaks.get('hbm_gbs', 6650.0)
-        peak_src = 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s'
-    traffic, extra = None, {}
-    try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/traffic.json)
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dominant, {})
-        traffic = tj.get('traffic_bytes')
-        extra = {k: v for k, v in tj.items() if k != 'traffic_bytes'}
+    src = 'MEASURED_PEAKS.json' if peaks else 'fallback (B200_PROFILING.md)'
+    sm_clk = peaks.get('sm_max_mhz', 1965.0) * 1e6
+    PEAK = {'tensor': (peaks.get('bf16_tflops_sustained', 1400.0), 'TFLOP/s', 1e12, src + ' bf16_tflops_sustained'),
+            'hbm': (peaks.get('hbm_gbs', 6650.0), 'GB/s', 1e9, src + ' hbm_gbs'),
+            # fp32 issue slots: 148 SMs x 128 lanes x clock, at the formulation's minimum of 8 instructions per triplet
+            'issue': (148 * 128 * sm_clk / 8.0 / 1e9, 'Gtriplet/s', 1e9, '148 SMs x 128 fp32 lanes x %.0f MHz / 8 instr per triplet' % (sm_clk / 1e6))}
+    traffic_tab = {}
+    try:  # DRAM bytes per launch from the committed `ncu --set full` capture (profiles/traffic.json)
+        traffic_tab = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
     except (OSError, ValueError):
         pass
-    roofline = {'kernel': dominant, 'bound': bound, 'achieved': achieved, 'peak': peak, 'unit': unit, 'frac': achieved / peak,
-                'traffic': traffic, 'algorithmic_work': work, 'ncu': extra, 'peak_source': peak_src,
+    table = {}
+    for tag, t_ms in prof.items():
+        bound, work = kernel_work(tag, w, stats)
+        row = {'ms': t_ms, 'share_of_serialised_step': t_ms / sum(prof.values())}
+        if bound:
+            peak, unit, scale, psrc = PEAK[bound]
+            ach = work / (t_ms * 1e-3) / scale
+            row.update(bound=bound, work=work, achieved=ach, peak=peak, unit=unit, frac=ach / peak)
+        table[tag] = row
+    dominant = max(prof, key=prof.get)
+    d = table[dominant]
+    tj = traffic_tab.get(dominant, {}) if args.config == 'C2' else {}
+    roofline = {'kernel': dominant, 'bound': d.get('bound', 'latency'), 'achieved': d.get('achieved'), 'peak': d.get('peak'),
+                'unit': d.get('unit'), 'frac': d.get('frac'), 'traffic': tj.get('traffic_bytes'), 'algorithmic_work': d.get('work'),
+                'ncu': {k: v for k, v in tj.items() if k != 'traffic_bytes'},
+                'peak_source': PEAK[d['bound']][3] if 'bound' in d else None,
                 'note': ('algorithmic FLOPs = 2*M*N*K; the kernel executes 3x that as bf16 MMAs (hi/lo split) for fp32 parity'
-                         if bound == 'tensor' else ''), 'avg_launch_ms': dur * 1e3,
-                'share_of_step': float(np.mean(dom_ms)) / (ms / K), 'launches_per_step': float(gpu_launches) / K}
+                         if d.get('bound') == 'tensor' else
+                         'valid triplets per launch; neither HBM- nor tensor-bound: the B^3 sweep runs out of registers' if d.get('bound') == 'issue' else ''),
+                'avg_launch_ms': d['ms'], 'share_of_step': d['ms'] / (ms / K),
+                'timing': 'CUDA events around each launch, step serialised on one stream, stream pre-loaded (device time only)'}
 
     if rank != 0:
         if world > 1:
@@ -374,20 +448,22 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline:
         n = max(1, args.cpu_steps)
-        xs, ls = make_data((n + 1) * B, seed=1)
-        ts = cpu_steps(xs, ls, n, 1)
+        xs, ls = make_data(w, (n + 1) * B, seed=1)
+        ts = cpu_steps(w, xs, ls, n, 1)
         cpu_baseline = {'value': n * B / float(np.sum(ts)), 'unit': 'articles/s', 'cores': os.cpu_count(), 'kind': 'port',
                         'sample': '%d steps of B=%d after 1 warm-up step, reference algorithm restated on PyTorch-CPU (%s)'
                                   % (n, B, cpu_info())}
 
+    state_mb = (3 * (F * H + F + H) * 4 + 2 * F * ((H + 64) // 64 * 64) * 2 + 2 * B * ((F + 31) // 32 * 32) * 2) / 1e6
     out = {
         'metric': 'articles/sec', 'value': value, 'unit': 'articles/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
+        'data': 'real (UCI news fixture tests/golden/uci_c1.npz)' if w['kind'] == 'uci' else 'synthetic',
         'config': {'workload': w['name'], 'global_batch': B * world, 'rows_per_rank': n_rows, 'parallelism': 'dp%d' % world,
-                   'l2': ('flushed between steps (256 MB write), per-step events' if args.flush_l2 else
-                          'inputs larger than L2: every step reads batch rows not touched since the previous epoch; dataset CSR '
-                          '+ per-step state (W, Z, grad ~ 92 MB) exceed the 126 MB L2'),
+                   'l2': 'inputs larger than L2: every step gathers %d fresh rows of the %.0f MB device-resident set (CSR + corrupted values) '
+                         'and streams %.0f MB of parameter / gradient / operand state; L2 is 126 MB'
+                         % (B * (3 if explicit else 1), csr.h2d_bytes / 1e6 + csr.nnz * 4 / 1e6, state_mb),
+                   'window': 'K steps from an epoch boundary: one corruption pass over the set and one permutation inside',
                    'loss_first_last': [float(losses[0, 0]), float(losses[-1, 0])],
                    'launch': 'cuda graph replay' if use_graph else 'eager', 'grad_exchange': eng.allreduce_mode},
         'clocks': clk,
@@ -395,7 +471,8 @@ def main():
                 'api': 'TrainEngine.run_feed(HostFeed) per step: pinned host batch -> H2D -> step -> D2H scalars, synchronised'},
         'gpu_launches': gpu_launches,
         'roofline': roofline,
-        'kernels_ms_per_step': prof,
+        'kernels': table,
+        'batch_stats': stats,
         'cpu_baseline': cpu_baseline,
     }
     print(json.dumps(out))

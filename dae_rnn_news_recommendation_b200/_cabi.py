@@ -30,6 +30,9 @@ _SIGNATURES = {
     'dae_version': (C.c_int, []),
     'dae_last_error': (C.c_int, [C.c_char_p, sz]),
     'dae_batch_prepare': (C.c_int, [p, i64, p, i32, p, i32, p, p, p, p, p, p, p]),
+    'dae_batch_prepare_next': (C.c_int, [p, i64, i64, p, i32, p, i32, p, p, p, p, p, p, p]),
+    'dae_batch_commit': (C.c_int, [i32, p, p, p, p, p, p, p, p, p, p, p, p, p]),
+    'dae_batch_prepare_explicit': (C.c_int, [p, i64, p, i32, i64, p, p, p]),
     'dae_step_advance': (C.c_int, [p, i64, p]),
     'dae_encode_csr_fwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p, i64, p]),
     'dae_col_scan': (C.c_int, [p, i32, p, p, p]),
@@ -39,9 +42,6 @@ _SIGNATURES = {
     'dae_split_bf16': (C.c_int, [p, i32, i32, i64, p, p, i64, i32, f32, p]),
     'dae_sym_split_bf16': (C.c_int, [p, i32, i64, f32, p, p, i64, p]),
     'dae_gemm_bf16x3': (C.c_int, [i32, i32, i32, f32, p, p, i64, i32, p, p, i64, i32, p, i64, i32, i32, p, i32, i32, p]),
-    'dae_gemm_bf16x3_tune': (C.c_int, [i32, p, i32, i32, i32, f32, p, p, i64, i32, p, p, i64, i32, p, i64, i32, i32, p, i32, i32, p]),
-    'dae_debug_set_trace': (C.c_int, [p]),
-    'dae_gemm_set_cluster_mode': (C.c_int, [i32]),
     'dae_decode_fused_bf16x3': (C.c_int, [i32, i32, i32, p, p, i64, p, p, i64, p, p, p, p, p, i32, i32, p, p, p, p, i64, p, p, p]),
     'dae_reduce_parts': (C.c_int, [p, i32, i32, p, p]),
     'dae_decode_loss_bwd': (C.c_int, [p, p, p, p, i32, i32, p, i32, i32, p, p, p, i64, p, p]),

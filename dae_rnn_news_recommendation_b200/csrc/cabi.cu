@@ -32,8 +32,9 @@ constexpr int kMaxB = 4096;
 __global__ void __launch_bounds__(1024) batch_prepare_kernel(
     const int32_t* __restrict__ perm, int64_t offset, const int64_t* __restrict__ ctl, int B, const float* __restrict__ labels_all,
     int strategy, int32_t* __restrict__ rows_out, float* __restrict__ labels_out, int32_t* seg_lo,
-    int32_t* seg_hi, float* __restrict__ weight_out, double* __restrict__ stats) {
+    int32_t* seg_hi, float* __restrict__ weight_out, double* __restrict__ stats, int64_t n_perm) {
   if (ctl) offset += ctl[0];  // device-resident batch cursor (CUDA-graph replay)
+  if (n_perm > 0 && offset + B > n_perm) return;  // staging the batch AFTER the epoch's last one: nothing to prepare
   __shared__ float keys[kMaxB];
   __shared__ int vals[kMaxB];
   __shared__ double red[32];
@@ -154,6 +155,32 @@ __global__ void batch_rows_kernel(const int32_t* __restrict__ perm, int64_t offs
   if (i < DAE_STAT_SLOTS) stats[i] = (i == DAE_STAT_SUM_W) ? (double)B : 0.0;
 }
 
+// staged batch (prepared on a side branch during the previous step) -> the live per-batch buffers
+__global__ void batch_commit_kernel(int B, const int32_t* __restrict__ rows_s, const float* __restrict__ labels_s,
+                                    const int32_t* __restrict__ seg_lo_s, const int32_t* __restrict__ seg_hi_s,
+                                    const float* __restrict__ weight_s, const double* __restrict__ stats_s, int32_t* __restrict__ rows,
+                                    float* __restrict__ labels_b, int32_t* __restrict__ seg_lo, int32_t* __restrict__ seg_hi,
+                                    float* __restrict__ weight, double* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) { rows[i] = rows_s[i]; labels_b[i] = labels_s[i]; seg_lo[i] = seg_lo_s[i]; seg_hi[i] = seg_hi_s[i]; weight[i] = weight_s[i]; }
+  if (i < DAE_STAT_SLOTS) stats[i] = stats_s[i];
+}
+
+// explicit (org, pos, neg) triplets: the three row blocks of the stacked [org; pos; neg] matrix for batch perm[offset : offset+B]
+// (autoencoder/utils.py:73-91 gen_batches_triplet); each of the three reconstruction terms is a mean over B rows.
+__global__ void batch_rows_explicit_kernel(const int32_t* __restrict__ perm, int64_t offset, const int64_t* __restrict__ ctl, int B,
+                                           int64_t n_each, int32_t* __restrict__ rows_out, double* __restrict__ stats) {
+  if (ctl) offset += ctl[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    const int64_t r = perm ? (int64_t)perm[offset + i] : offset + i;
+    rows_out[i] = (int32_t)r;
+    rows_out[B + i] = (int32_t)(r + n_each);
+    rows_out[2 * B + i] = (int32_t)(r + 2 * n_each);
+  }
+  if (i < DAE_STAT_SLOTS) stats[i] = (i == DAE_STAT_SUM_W) ? (double)B : 0.0;
+}
+
 __global__ void step_advance_kernel(int64_t* ctl, int64_t row_stride) {
   ctl[0] += row_stride;  // batch cursor into the epoch permutation
   ctl[1] += 1;           // row of the per-epoch stats log
@@ -183,7 +210,38 @@ extern "C" int dae_batch_prepare(const int32_t* perm, int64_t offset, const int6
   DAE_REQUIRE(seg_lo && seg_hi, "dae_batch_prepare: null segment outputs");
   DAE_REQUIRE(strategy == DAE_TRIPLET_NONE || labels_all, "dae_batch_prepare: labels required for triplet strategies");
   dae::batch_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(perm, offset, ctl, B, labels_all, strategy, rows_out,
-                                                                 labels_out, seg_lo, seg_hi, weight_out, stats);
+                                                                 labels_out, seg_lo, seg_hi, weight_out, stats, 0);
   DAE_CHECK_LAUNCH("dae_batch_prepare");
+  return DAE_OK;
+}
+
+extern "C" int dae_batch_prepare_next(const int32_t* perm, int64_t n_perm, int64_t stride, const int64_t* ctl, int32_t B,
+                                      const float* labels_all, int32_t strategy, int32_t* rows_s, float* labels_s, int32_t* seg_lo_s,
+                                      int32_t* seg_hi_s, float* weight_s, double* stats_s, void* stream) {
+  DAE_REQUIRE(ctl && n_perm > 0 && B >= 1 && B <= dae::kMaxB && rows_s && seg_lo_s && seg_hi_s && stats_s && labels_all,
+              "dae_batch_prepare_next: bad arguments");
+  DAE_REQUIRE(strategy == DAE_TRIPLET_BATCH_ALL || strategy == DAE_TRIPLET_BATCH_HARD, "dae_batch_prepare_next: triplet strategies only");
+  dae::batch_prepare_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(perm, stride, ctl, B, labels_all, strategy, rows_s, labels_s, seg_lo_s,
+                                                                 seg_hi_s, weight_s, stats_s, n_perm);
+  DAE_CHECK_LAUNCH("dae_batch_prepare_next");
+  return DAE_OK;
+}
+
+extern "C" int dae_batch_commit(int32_t B, const int32_t* rows_s, const float* labels_s, const int32_t* seg_lo_s, const int32_t* seg_hi_s,
+                                const float* weight_s, const double* stats_s, int32_t* rows, float* labels_b, int32_t* seg_lo,
+                                int32_t* seg_hi, float* weight, double* stats, void* stream) {
+  DAE_REQUIRE(B >= 1 && rows_s && labels_s && seg_lo_s && seg_hi_s && weight_s && stats_s && rows && labels_b && seg_lo && seg_hi && weight && stats,
+              "dae_batch_commit: null pointer");
+  dae::batch_commit_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(B, rows_s, labels_s, seg_lo_s, seg_hi_s, weight_s, stats_s, rows,
+                                                                           labels_b, seg_lo, seg_hi, weight, stats);
+  DAE_CHECK_LAUNCH("dae_batch_commit");
+  return DAE_OK;
+}
+
+extern "C" int dae_batch_prepare_explicit(const int32_t* perm, int64_t offset, const int64_t* ctl, int32_t B, int64_t n_each,
+                                          int32_t* rows_out, double* stats, void* stream) {
+  DAE_REQUIRE(B >= 1 && n_each >= 1 && rows_out && stats, "dae_batch_prepare_explicit: bad arguments");
+  dae::batch_rows_explicit_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, offset, ctl, B, n_each, rows_out, stats);
+  DAE_CHECK_LAUNCH("dae_batch_prepare_explicit");
   return DAE_OK;
 }

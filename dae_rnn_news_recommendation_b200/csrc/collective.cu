@@ -58,11 +58,26 @@ __global__ void __launch_bounds__(512) allreduce_multimem_kernel(float* __restri
   const int64_t per = (n4 + world - 1) / world;
   const int64_t lo = (int64_t)rank * per;
   const int64_t hi = (lo + per < n4) ? lo + per : n4;
-  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
-    float* p = mc + (i << 2);
-    float a, b, c, d;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p) : "memory");
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  // kUnroll independent in-switch reductions in flight per thread (each is a round trip GPU -> switch -> P GPUs -> switch -> GPU),
+  // then their broadcasts
+  constexpr int kUnroll = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kUnroll) {
+    float v[kUnroll][4];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int64_t i = i0 + k * stride;
+      if (i < hi)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[k][0]), "=f"(v[k][1]), "=f"(v[k][2]), "=f"(v[k][3]) : "l"(mc + (i << 2)) : "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const int64_t i = i0 + k * stride;
+      if (i < hi)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + (i << 2)), "f"(v[k][0]), "f"(v[k][1]), "f"(v[k][2]),
+                     "f"(v[k][3]) : "memory");
+    }
   }
   if (rank == 0 && blockIdx.x == 0 && (n4 << 2) + (int64_t)threadIdx.x < n) {
     float* p = mc + (n4 << 2) + threadIdx.x;

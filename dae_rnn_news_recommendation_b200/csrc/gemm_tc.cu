@@ -53,8 +53,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Spin, then back off with nanosleep; a wait that lasts longer than ~4 s (a lost TMA / commit: a programming error, not a
+// slow peer) traps so the failure surfaces on the host at the next synchronisation instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 4096u) {
+      __nanosleep(64);
+      if (spins > (1u << 26)) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -67,24 +74,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
-}
-// multicast variant: the box lands at the same smem offset of every CTA in cta_mask and completes tx on each one's mbarrier
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// commit that arrives on the mbarrier at this smem offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -142,8 +131,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int block_n, bool a_mn, bool b
 // ---------------------------------------------------------------------------------------------------------------------
 struct GemmParams {
   int M, N, K;           // logical sizes (TMA zero-fills out-of-range rows / columns)
-  int k_splits;          // > 1: split-K
-  int atomic;            // accumulate into C with fp32 atomics (split-K, or C += ...)
+  int k_splits;          // > 1: uniform split-K
+  int stream_k;          // 1: stream-K -- the CTAs share the (tile, k-block) units evenly, partial tiles are added with atomics
+  int atomic;            // accumulate into C with fp32 atomics (split-K / stream-K, or C += ...)
   int a_mn, b_mn;        // operand majorness
   float alpha;
   float* C;              // EPI_STORE: fp32 output [M x ldc]
@@ -157,15 +147,55 @@ struct GemmParams {
   __nv_bfloat16* dz_hi; __nv_bfloat16* dz_lo; int64_t ld_dz;
   float* row_loss_part;  // [M] row losses, accumulated with fp32 atomics (zeroed by the launcher)
   const int32_t* tile_ptr; // [M x (2 * n_tiles_n + 1)]: first CSR entry of every half tile, relative to the row start
-  long long* trace;      // optional clock64 trace of CTA 0 (debug)
 };
 
 enum { EPI_STORE = 0, EPI_DECODE = 1 };
 
-// epilogue warps: EW / 4 warps per TMEM lane quarter, each takes 1/(EW/4) of the tile's columns (store epilogue: 8, fused
-// decode epilogue: 8 -- measured: 16 warps do not help, the epilogue is bound by global store requests, not by issue slots)
+// epilogue warps: EW / 4 warps per TMEM lane quarter, each takes 1/(EW/4) of the tile's columns
 constexpr int kEwStore = 8, kEwDecode = 8;
 constexpr int tc_threads(int ew) { return 128 + 32 * ew; }  // warps 0-3: TMA / MMA / TMEM-alloc / spare; then the epilogue warps
+
+// Work distribution, walked identically by the TMA producer, the MMA issuer and the epilogue warps of a CTA.
+//   classic : work item w = (tile, k split), items blockIdx.x, blockIdx.x + gridDim.x, ...
+//   stream-K: the tiles x k-blocks units are cut into gridDim.x equal contiguous ranges; a CTA's range covers the tail of one
+//             tile, whole tiles, and the head of another -- every segment is one accumulator pass + one (atomic) epilogue.
+//             Balances shapes whose tile count does not fill the 148 SMs evenly (dW: 158 tiles) without shrinking the tiles.
+struct Sched {
+  int tiles_m, tiles, kb_total, kb_per_split, n_work, stream, w;
+  long long u, u_end;
+  __device__ __forceinline__ void init(const GemmParams& p, int block_n) {
+    tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    tiles = tiles_m * ((p.N + block_n - 1) / block_n);
+    kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+    stream = p.stream_k;
+    kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
+    n_work = tiles * p.k_splits;
+    w = blockIdx.x;
+    const long long U = (long long)tiles * kb_total;
+    u = (long long)blockIdx.x * U / gridDim.x;
+    u_end = (long long)(blockIdx.x + 1) * U / gridDim.x;
+  }
+  __device__ __forceinline__ bool next(int& mb, int& nb, int& kb0, int& kb1) {
+    int tile;
+    if (stream) {
+      if (u >= u_end) return false;
+      tile = (int)(u / kb_total);
+      kb0 = (int)(u - (long long)tile * kb_total);
+      const long long left = u_end - u;
+      kb1 = (left < (long long)(kb_total - kb0)) ? kb0 + (int)left : kb_total;
+      u += kb1 - kb0;
+    } else {
+      if (w >= n_work) return false;
+      tile = w % tiles;
+      kb0 = (w / tiles) * kb_per_split;
+      kb1 = min(kb_total, kb0 + kb_per_split);
+      w += gridDim.x;
+    }
+    mb = tile % tiles_m;
+    nb = tile / tiles_m;
+    return true;
+  }
+};
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -174,12 +204,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float f_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+constexpr float kLog2e = 1.4426950408889634f;
 
 // decoder activation on the MUFU pipe (relative error ~1e-6, inside the 1e-4 parity budget)
 template <int ACT>
 __device__ __forceinline__ float act_fast(float z) {
-  if (ACT == DAE_ACT_SIGMOID) return f_rcp(1.0f + f_ex2(-1.4426950408889634f * z));
-  if (ACT == DAE_ACT_TANH) return 1.0f - 2.0f * f_rcp(1.0f + f_ex2(2.8853900817779268f * z));
+  if (ACT == DAE_ACT_SIGMOID) return f_rcp(1.0f + f_ex2(-kLog2e * z));
+  if (ACT == DAE_ACT_TANH) return 1.0f - 2.0f * f_rcp(1.0f + f_ex2(2.0f * kLog2e * z));
   return z;
 }
 
@@ -192,10 +223,79 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 
-// CL = 2: two CTAs of a cluster work on tiles (2*mp, nb) and (2*mp+1, nb): they share the B tile, each loads half of it and TMA
-// multicasts it into both CTAs' shared memory (1/3 less L2 -> SM operand traffic); MMAs stay cta_group::1, the stage-free
-// (empty) barriers collect one tcgen05.commit from each CTA.
-template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS, int CL>
+// r[j] for a runtime j in [0,16) without dynamic register indexing
+__device__ __forceinline__ float select16(const uint32_t (&r)[16], int j) {
+  uint32_t v = r[0];
+#pragma unroll
+  for (int k = 1; k < 16; ++k) v = (j == k) ? r[k] : v;
+  return __uint_as_float(v);
+}
+
+// One 16-column chunk of the fused decode epilogue, evaluated as if every target x were 0 (99 % of a bag-of-words row is):
+// z = acc + bv -> D = g(z) -> loss term -> dZ = sc * dloss/dz, packed as bf16 hi / lo pairs.  `lsum`: CE in log2 units, MSE plain.
+template <int ACT, int LOSS>
+__device__ __forceinline__ void decode_chunk_generic(const uint32_t (&r)[16], const float* __restrict__ bias, float sc, bool edge,
+                                                     int n_lim, int nc, uint32_t (&hpk)[8], uint32_t (&lpk)[8], float& lsum) {
+#pragma unroll
+  for (int j2 = 0; j2 < 8; ++j2) {
+    float dzp[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = 2 * j2 + e;
+      const float z = __uint_as_float(r[j]) + bias[j];
+      const float d = act_fast<ACT>(z);
+      float dz, lt;
+      if (LOSS == DAE_LOSS_CE) {
+        const float omd = 1.0f - d;
+        const float b = omd + kEps;                 // 1. - decode + 1e-16, left to right (:269)
+        lt = -f_lg2(b);
+        // dl * g' = d * omd / b; omd / b == 1 exactly in fp32 unless omd == 0 (then the product is 0)
+        dz = (ACT == DAE_ACT_SIGMOID) ? ((omd != 0.0f) ? sc * d : 0.0f) : sc * act_grad_from_y<ACT>(d) * f_rcp(b);
+      } else {
+        lt = d * d;
+        dz = 2.0f * sc * d * act_grad_from_y<ACT>(d);
+      }
+      if (edge) { const bool in = (nc + j < n_lim); lt = in ? lt : 0.0f; dz = in ? dz : 0.0f; }  // uniform branch
+      lsum += lt;
+      dzp[e] = dz;
+    }
+    const uint32_t hp = pack_bf16(dzp[0], dzp[1]);
+    hpk[j2] = hp;
+    lpk[j2] = pack_bf16(dzp[0] - __uint_as_float(hp << 16), dzp[1] - __uint_as_float(hp & 0xffff0000u));
+  }
+}
+
+// sigmoid + cross-entropy fast path (x = 0): with t = e^z,  1 - D = 1/(1+t),  -log(1 - D) = log(1+t),  dZ = sc * t/(1+t).
+// Four columns share ONE reciprocal (Montgomery batch inversion of P = prod(1+t)) and ONE logarithm (log2 P): 1.5 MUFU per
+// element instead of 3.  Valid while every z <= 10 (P <= e^10 bounds each factor, all factors being >= 1): there the fp32
+// reference's own `1 - decode` rounding (2^-25 / (1 - D) relative) stays far below the parity budget; the caller re-evaluates the
+// chunk with decode_chunk_generic when this returns false.
+__device__ __forceinline__ bool decode_chunk_sigmoid_ce(const uint32_t (&r)[16], const float* __restrict__ biasc, float sc,
+                                                        uint32_t (&hpk)[8], uint32_t (&lpk)[8], float& lsum) {
+  bool ok = true;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float t[4], a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      t[j] = f_ex2(fmaf(__uint_as_float(r[4 * g + j]), kLog2e, biasc[4 * g + j]));   // biasc = bv * log2(e)
+      a[j] = 1.0f + t[j];
+    }
+    const float p01 = a[0] * a[1], p23 = a[2] * a[3], P = p01 * p23;
+    ok = ok && (P <= 22026.0f);                         // false for NaN / inf as well
+    const float Rs = f_rcp(P) * sc;
+    lsum += f_lg2(P);
+    const float r23 = Rs * p23, r01 = Rs * p01;
+    const float dz0 = t[0] * (r23 * a[1]), dz1 = t[1] * (r23 * a[0]), dz2 = t[2] * (r01 * a[3]), dz3 = t[3] * (r01 * a[2]);
+    const uint32_t h0 = pack_bf16(dz0, dz1), h1 = pack_bf16(dz2, dz3);
+    hpk[2 * g] = h0; hpk[2 * g + 1] = h1;
+    lpk[2 * g] = pack_bf16(dz0 - __uint_as_float(h0 << 16), dz1 - __uint_as_float(h0 & 0xffff0000u));
+    lpk[2 * g + 1] = pack_bf16(dz2 - __uint_as_float(h1 << 16), dz3 - __uint_as_float(h1 & 0xffff0000u));
+  }
+  return ok;
+}
+
+template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
 __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore), 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                                                                       const __grid_constant__ CUtensorMap tm_a_lo,
                                                                       const __grid_constant__ CUtensorMap tm_b_hi,
@@ -207,31 +307,25 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
   constexpr int kEpiWarps = (EPI == EPI_DECODE) ? kEwDecode : kEwStore;
   constexpr int kParts = kEpiWarps / 4;          // column parts per tile (one per epilogue warp of a lane quarter)
   constexpr int HALF_N = BLOCK_N / kParts;       // columns handled by one epilogue warp
+  constexpr bool kFast = (EPI == EPI_DECODE) && (ACT == DAE_ACT_SIGMOID) && (LOSS == DAE_LOSS_CE);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[kAccStages], tmem_empty_bar[kAccStages];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_bias[kAccStages][BLOCK_N];
+  __shared__ float s_bias[EPI == EPI_DECODE ? kAccStages : 1][EPI == EPI_DECODE ? BLOCK_N : 1];
+  __shared__ float s_biasc[kFast ? kAccStages : 1][kFast ? BLOCK_N : 1];   // bv * log2(e) for the sigmoid/CE fast path
   __shared__ __align__(16) float s_tr[EPI == EPI_STORE ? kEpiWarps : 1][32][20];  // per-warp transpose staging for coalesced stores
   __shared__ __align__(16) uint8_t s_stage[EPI == EPI_DECODE ? kEpiWarps : 1][2][32][48];  // bf16 hi / lo dZ blocks [32 rows x 16 cols], rows padded to 48 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int kblocks_total = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int kb_per_split = (kblocks_total + p.k_splits - 1) / p.k_splits;
-  // work items are (m-tile group of CL tiles, n tile, k split); the CTAs of a cluster take the CL m-tiles of one group.
-  // A CTA whose m-tile is past the end still runs the pipeline (TMA zero-fills, the epilogue stores nothing).
-  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-  const int tiles_m = (((p.M + BLOCK_M - 1) / BLOCK_M) + CL - 1) / CL;   // m-tile GROUPS
-  const int n_work = tiles_m * tiles_n * p.k_splits;
-  const int w_begin = blockIdx.x / CL, w_step = gridDim.x / CL;
-#define DAE_MB(w) (((w) % tiles_m) * CL + (int)crank)
+  Sched sched;
+  sched.init(p, BLOCK_N);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiWarps); }
     fence_barrier_init();
   }
@@ -240,7 +334,7 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before anything multicasts
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -248,9 +342,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = w_begin; w < n_work; w += w_step) {
-        const int mb = DAE_MB(w), nb = (w / tiles_m) % tiles_n, ks = w / (tiles_m * tiles_n);
-        const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+      int mb, nb, kb0, kb1;
+      while (sched.next(mb, nb, kb0, kb1)) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa_hi = smem + stage * STAGE_BYTES;
@@ -268,29 +361,14 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
               tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mb * BLOCK_M + j * 64, kb * BLOCK_K);
             }
           }
-          if (CL == 1) {
-            if (!p.b_mn) {
-              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, nb * BLOCK_N);
-              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, nb * BLOCK_N);
-            } else {
+          if (!p.b_mn) {
+            tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, nb * BLOCK_N);
+            tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, nb * BLOCK_N);
+          } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j) {
-                tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
-                tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
-              }
-            }
-          } else {   // this CTA fetches its half of the shared B tile and multicasts it to both CTAs of the cluster
-            constexpr int HN = BLOCK_N / 2;
-            if (!p.b_mn) {   // the B tensor maps of the cluster variant carry a box of BLOCK_N / 2 rows
-              tma_load_2d_mc(&tm_b_hi, &full_bar[stage], sb_hi + crank * HN * 128, kb * BLOCK_K, nb * BLOCK_N + crank * HN, 0x3);
-              tma_load_2d_mc(&tm_b_lo, &full_bar[stage], sb_lo + crank * HN * 128, kb * BLOCK_K, nb * BLOCK_N + crank * HN, 0x3);
-            } else {
-#pragma unroll
-              for (int jj = 0; jj < HN / 64; ++jj) {
-                const int j = crank * (HN / 64) + jj;
-                tma_load_2d_mc(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K, 0x3);
-                tma_load_2d_mc(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K, 0x3);
-              }
+            for (int j = 0; j < BLOCK_N / 64; ++j) {
+              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -303,20 +381,14 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
       const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      long long* trace = (blockIdx.x == 0) ? p.trace : nullptr;
-      int tr_i = 0;
-      for (int w = w_begin; w < n_work; w += w_step) {
-        const int ks = w / (tiles_m * tiles_n);
-        const int kb0 = ks * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
-        if (trace && tr_i < 500) trace[tr_i++] = clock64();
+      int mb, nb, kb0, kb1;
+      while (sched.next(mb, nb, kb0, kb1)) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        if (trace && tr_i < 500) trace[tr_i++] = clock64();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (trace && tr_i < 500) trace[tr_i++] = clock64();
           const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sa_lo = sa_hi + A_TILE, sb_hi = sa_lo + A_TILE, sb_lo = sb_hi + B_TILE;
           const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
@@ -332,14 +404,12 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
             umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
             umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
           }
-          if (CL == 1) umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
-          else umma_commit_mc(&empty_bar[stage], 0x3);      // ... in BOTH CTAs: the peer's multicast writes into this stage too
+          umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
           if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
-      if (trace && tr_i < 500) trace[tr_i++] = clock64();
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -347,22 +417,22 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     const int quarter = ew & 3;              // TMEM lane quarter this warp may access (warp id % 4)
     const int half = ew >> 2;                // which column part of the tile
     const int row_in_tile = quarter * 32 + lane;
+    const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     int acc = 0; uint32_t acc_phase = 0;
-    long long* trace = (blockIdx.x == 0 && ew == 0 && lane == 0) ? p.trace : nullptr;
-    int tr_i = 500;
-    for (int w = w_begin; w < n_work; w += w_step) {
-      const int mb = DAE_MB(w), nb = (w / tiles_m) % tiles_n;
+    int mb, nb, kb0, kb1;
+    while (sched.next(mb, nb, kb0, kb1)) {
       const int m = mb * BLOCK_M + row_in_tile;
       const int n0 = nb * BLOCK_N + half * HALF_N;
       if (EPI == EPI_DECODE) {  // stage this tile's visible-bias slice (named barrier 1: the epilogue threads)
-        for (int j = threadIdx.x - 128; j < BLOCK_N; j += 32 * kEpiWarps)
-          s_bias[acc][j] = (nb * BLOCK_N + j < p.N) ? p.bv[nb * BLOCK_N + j] : 0.0f;
+        for (int j = threadIdx.x - 128; j < BLOCK_N; j += 32 * kEpiWarps) {
+          const float b = (nb * BLOCK_N + j < p.N) ? p.bv[nb * BLOCK_N + j] : 0.0f;
+          s_bias[acc][j] = b;
+          if (kFast) s_biasc[acc][j] = b * kLog2e;
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
-      if (trace && tr_i < 1000) trace[tr_i++] = clock64();
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      if (trace && tr_i < 1000) trace[tr_i++] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * HALF_N;
 
       if (EPI == EPI_STORE) {
@@ -414,9 +484,9 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
       } else {
         // ---- fused decode epilogue: D = g(Z + bv); row loss; dZ -> bf16 hi/lo (autoencoder.py:411, triplet_loss_utils.py:269-275)
         // 99 % of a bag-of-words target row is zero, so each 16-column chunk is first evaluated branch-free as if x == 0,
-        // stored, and then the row's few stored entries inside the chunk are re-evaluated exactly and patched in place.  The clean CSR row is walked with a cursor (columns are sorted).
-        // The cursor keeps the next THREE entries (c0,v0),(c1,v1),(c2,v2) in registers, loaded well before they are needed, so
-        // the L2 latency of the CSR stream never sits on the column loop.
+        // stored, and then the row's few stored entries inside the chunk are re-evaluated exactly and patched in place.  The clean
+        // CSR row is walked with a cursor (columns are sorted) that keeps the next THREE entries (c0,v0),(c1,v1),(c2,v2) in
+        // registers, loaded well before they are needed, so the L2 latency of the CSR stream never sits on the column loop.
         int64_t pc = 0, pe = 0;
         int c0 = 0x7fffffff, c1 = 0x7fffffff, c2 = 0x7fffffff;
         float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
@@ -431,6 +501,7 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
           if (pc + 2 < pe) { c2 = p.indices[pc + 2]; v2 = p.values[pc + 2]; }
           sc = (p.weight ? p.weight[m] : 1.0f) / ((float)p.stats[DAE_STAT_SUM_W] + kEps);
         }
+        const float inv_sc = (sc != 0.0f) ? 1.0f / sc : 0.0f;
         const bool edge = (n0 + HALF_N > p.N);   // only the last column tile has out-of-range columns
         float lsum = 0.0f;   // CE: accumulated in log2 units, scaled by ln2 at the end
         // dZ leaves through a per-warp shared-memory transpose: each thread (= batch row) drops the bf16 hi and lo parts of its
@@ -449,34 +520,14 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
           const int nc = n0 + c * 16;
           if (m < p.M) {
             const float* bias = &s_bias[acc][half * HALF_N + c * 16];
-            float zz[16];
             uint32_t hpk[8], lpk[8];
-#pragma unroll
-            for (int j2 = 0; j2 < 8; ++j2) {
-              float dzp[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int j = 2 * j2 + e;
-                zz[j] = __uint_as_float(r[j]) + bias[j];
-                const float d = act_fast<ACT>(zz[j]);
-                float dz, lt;
-                if (LOSS == DAE_LOSS_CE) {
-                  const float omd = 1.0f - d;
-                  const float b = omd + kEps;                 // 1. - decode + 1e-16, left to right (:269)
-                  lt = -f_lg2(b);
-                  // dl * g' = d * omd / b; omd / b == 1 exactly in fp32 unless omd == 0 (then the product is 0)
-                  dz = (ACT == DAE_ACT_SIGMOID) ? ((omd != 0.0f) ? sc * d : 0.0f) : sc * act_grad_from_y<ACT>(d) * f_rcp(b);
-                } else {
-                  lt = d * d;
-                  dz = 2.0f * sc * d * act_grad_from_y<ACT>(d);
-                }
-                if (edge) { const bool in = (nc + j < n_lim); lt = in ? lt : 0.0f; dz = in ? dz : 0.0f; }  // uniform branch
-                lsum += lt;
-                dzp[e] = dz;
-              }
-              const uint32_t hp = pack_bf16(dzp[0], dzp[1]);
-              hpk[j2] = hp;
-              lpk[j2] = pack_bf16(dzp[0] - __uint_as_float(hp << 16), dzp[1] - __uint_as_float(hp & 0xffff0000u));
+            bool fast_ok = false;   // this chunk went through the sigmoid/CE fast path: staged dZ = sc * D exactly
+            if (kFast && !edge) {
+              const float l0 = lsum;
+              fast_ok = decode_chunk_sigmoid_ce(r, &s_biasc[acc][half * HALF_N + c * 16], sc, hpk, lpk, lsum);
+              if (!fast_ok) { lsum = l0; decode_chunk_generic<ACT, LOSS>(r, bias, sc, edge, n_lim, nc, hpk, lpk, lsum); }
+            } else {
+              decode_chunk_generic<ACT, LOSS>(r, bias, sc, edge, n_lim, nc, hpk, lpk, lsum);
             }
             uint4* sh = reinterpret_cast<uint4*>(stg_hi + lane * 48);
             uint4* sl = reinterpret_cast<uint4*>(stg_lo + lane * 48);
@@ -486,10 +537,11 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
             while (c0 < nc + 16) {
               const float x = v0;
               const int j = c0 - nc;
-              float zj = zz[0];                               // zz[j] without dynamic register indexing
-#pragma unroll
-              for (int k = 1; k < 16; ++k) zj = (j == k) ? zz[k] : zj;
-              const float d = act_fast<ACT>(zj);
+              __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(stg_hi + lane * 48) + j;
+              __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(stg_lo + lane * 48) + j;
+              float d;
+              if (kFast && fast_ok && sc != 0.0f) d = (__bfloat162float(*ph) + __bfloat162float(*pl)) * inv_sc;   // D back from the staged sc * D
+              else d = act_fast<ACT>(select16(r, j) + bias[j]);
               const float gp = act_grad_from_y<ACT>(d);
               float dz;
               if (LOSS == DAE_LOSS_CE) {
@@ -503,8 +555,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
                 dz = -2.0f * sc * e2 * gp;
               }
               const __nv_bfloat16 hb = __float2bfloat16_rn(dz);
-              reinterpret_cast<__nv_bfloat16*>(stg_hi + lane * 48)[j] = hb;
-              reinterpret_cast<__nv_bfloat16*>(stg_lo + lane * 48)[j] = __float2bfloat16_rn(dz - __bfloat162float(hb));
+              *ph = hb;
+              *pl = __float2bfloat16_rn(dz - __bfloat162float(hb));
               ++pc;
               c0 = c1; v0 = v1; c1 = c2; v1 = v2;
               c2 = 0x7fffffff;
@@ -530,18 +582,16 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (trace && tr_i < 1000) trace[tr_i++] = clock64();
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer may still multicast / arrive here
+  __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
-#undef DAE_MB
 }
 
 // tile_ptr[m][t] = number of stored entries of batch row m with column < t * half_n (t = 0 .. n_half_tiles): where each
@@ -634,12 +684,32 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t o
 
 struct Operand { const void* hi; const void* lo; int64_t ld; int mn_major; };
 
-static int g_cluster_mode = -1;   // -1: read DAE_GEMM_CLUSTER on first use; 0 = single-CTA tiles; 1 = 2-CTA clusters with B multicast
+// cudaFuncSetAttribute is per device: remember which devices have been configured for this instantiation
+template <typename Kern>
+static int ensure_smem_attr(Kern kern, int smem, bool (&done)[64]) {
+  int dev = 0;
+  DAE_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
+  return DAE_OK;
+}
+
+static int sm_count() {
+  static int n[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
 
 template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
 static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStream_t st) {
-  if (g_cluster_mode < 0) { const char* e = getenv("DAE_GEMM_CLUSTER"); g_cluster_mode = (e && e[0] == '1') ? 1 : 0; }
-  const bool cl2 = (g_cluster_mode == 1) && (BLOCK_N == 256);
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   // K-major: tensor [rows=MN x cols=K], box {64 k, tile rows};  MN-major: tensor [rows=K x cols=MN], box {64 mn, 64 k}
@@ -651,8 +721,8 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
     if ((rc = make_map(&ta_lo, A.lo, p.M, p.K, A.ld, 64))) return rc;
   }
   if (!B.mn_major) {
-    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, cl2 ? BLOCK_N / 2 : BLOCK_N))) return rc;
-    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, cl2 ? BLOCK_N / 2 : BLOCK_N))) return rc;
+    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, BLOCK_N))) return rc;
+    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, BLOCK_N))) return rc;
   } else {
     if ((rc = make_map(&tb_hi, B.hi, p.N, p.K, B.ld, 64))) return rc;
     if ((rc = make_map(&tb_lo, B.lo, p.N, p.K, B.ld, 64))) return rc;
@@ -661,39 +731,28 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
   constexpr int smem = STAGES * (2 * BLOCK_M * BLOCK_K * 2 + 2 * BLOCK_N * BLOCK_K * 2) + 1024;
   constexpr int threads = tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore);
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  if (!cl2) {
-    auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS, 1>;
-    static bool attr = false;
-    if (!attr) { DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    const int tiles = tiles_m * tiles_n * p.k_splits;
-    const int grid = tiles < 148 ? tiles : 148;
-    kern<<<grid, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS>;
+  static bool attr_done[64] = {false};
+  if ((rc = ensure_smem_attr(kern, smem, attr_done))) return rc;
+  const int sms = sm_count();
+  int grid;
+  if (p.stream_k) {   // segments of at least ~6 k-blocks: a shorter main loop does not amortise its (atomic) epilogue
+    const long long units = (long long)tiles_m * tiles_n * kblocks;
+    long long g = units / 6;
+    if (g < 1) g = 1;
+    grid = (int)(g < sms ? g : sms);
   } else {
-    auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS, 2>;
-    static bool attr = false;
-    if (!attr) { DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
-    const int groups = ((tiles_m + 1) / 2) * tiles_n * p.k_splits;
-    const int clusters = groups < 74 ? groups : 74;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    DAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
+    const int items = tiles_m * tiles_n * p.k_splits;
+    grid = items < sms ? items : sms;
   }
+  kern<<<grid, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   return DAE_OK;
 }
 
 }  // namespace dae
 
 using namespace dae;
-
-static long long* g_debug_trace = nullptr;
-// diagnostic: the next tcgen05 launches write a clock64 trace of CTA 0 (MMA issuer at [0,500), epilogue warp 0 at [500,1000))
-extern "C" int dae_debug_set_trace(void* trace) { g_debug_trace = (long long*)trace; return DAE_OK; }
-// 0 = single-CTA tiles (default), 1 = 2-CTA clusters sharing the B tile through TMA multicast (128 x 256 tiles only)
-extern "C" int dae_gemm_set_cluster_mode(int32_t mode) { dae::g_cluster_mode = mode ? 1 : 0; return DAE_OK; }
 
 extern "C" int dae_split_bf16(const float* src, int32_t rows, int32_t cols, int64_t ld_src, void* hi, void* lo, int64_t ld_dst,
                               int32_t ones_col, float scale, void* stream) {
@@ -714,63 +773,50 @@ extern "C" int dae_sym_split_bf16(const float* G, int32_t B, int64_t ldg, float 
   return DAE_OK;
 }
 
-static int gemm_store_dispatch(int variant, long long* trace, int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi,
-                               const void* a_lo, int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
-                               int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col, float* special_out,
-                               int32_t k_splits, int32_t accumulate, void* stream) {
+extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
+                               int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
+                               int64_t ldc, int32_t n_store, int32_t special_col, float* special_out, int32_t k_splits,
+                               int32_t accumulate, void* stream) {
   DAE_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && M > 0 && N > 0 && K > 0, "dae_gemm_bf16x3: bad arguments");
   DAE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dae_gemm_bf16x3: operand leading dimensions must be multiples of 8 (TMA 16-byte strides)");
   DAE_REQUIRE(((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) % 16 == 0, "dae_gemm_bf16x3: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_store <= 0 || n_store > N) n_store = N;
-  if (k_splits < 1) k_splits = 1;
   const int kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+  const int tm = (M + 127) / 128, tn256 = (N + 255) / 256, tn128 = (N + 127) / 128;
+  const int sms = sm_count();
+  int stream_k = 0;
+  if (k_splits < 0) {   // auto: stream-K unless the 128 x 256 tiling already fills the SMs in whole waves
+    const int t = tm * tn256;
+    stream_k = (t % sms == 0) ? 0 : 1;
+    k_splits = 1;
+  }
+  if (k_splits < 1) k_splits = 1;
   if (k_splits > kblocks) k_splits = kblocks;
   {  // no empty splits
     const int per = (kblocks + k_splits - 1) / k_splits;
     k_splits = (kblocks + per - 1) / per;
   }
-  if (k_splits > 1 && !accumulate) {
+  const bool partial = (k_splits > 1) || stream_k;
+  if (partial && !accumulate) {
     DAE_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)n_store * sizeof(float), M, st));
     if (special_col >= 0 && special_out) DAE_CUDA(cudaMemsetAsync(special_out, 0, sizeof(float) * M, st));
   }
   GemmParams p{};
-  p.M = M; p.N = N; p.K = K; p.k_splits = k_splits; p.atomic = (k_splits > 1 || accumulate) ? 1 : 0; p.alpha = alpha;
+  p.M = M; p.N = N; p.K = K; p.k_splits = k_splits; p.stream_k = stream_k; p.atomic = (partial || accumulate) ? 1 : 0; p.alpha = alpha;
   p.C = C; p.ldc = ldc; p.n_store = n_store;
-  p.special_col = (special_out ? special_col : -1); p.special_out = special_out; p.trace = trace;
+  p.special_col = (special_out ? special_col : -1); p.special_out = special_out;
   Operand A{a_hi, a_lo, lda, a_mn_major}, B{b_hi, b_lo, ldb, b_mn_major};
+  // 128 x 256 tiles move fewer operand bytes per output, 128 x 128 tiles quantise better onto the SMs: pick the variant with the
+  // smaller (waves x relative tile cost).  Stream-K balances by construction, so it always takes the 128 x 256 tiles.
   int rc;
-  switch (variant) {
-    case 1: rc = launch_gemm<128, 3, EPI_STORE, 0, 0>(A, B, p, st); break;
-    case 2: rc = launch_gemm<128, 2, EPI_STORE, 0, 0>(A, B, p, st); break;
-    default: rc = launch_gemm<256, 2, EPI_STORE, 0, 0>(A, B, p, st); break;
-  }
+  const int tiles256 = tm * tn256 * k_splits, tiles128 = tm * tn128 * k_splits;
+  const float cost256 = 2.0f * (float)((tiles256 + sms - 1) / sms), cost128 = 1.1f * (float)((tiles128 + sms - 1) / sms);
+  if (!stream_k && cost128 < cost256) rc = launch_gemm<128, 3, EPI_STORE, 0, 0>(A, B, p, st);
+  else rc = launch_gemm<256, 2, EPI_STORE, 0, 0>(A, B, p, st);
   if (rc) return rc;
   DAE_CHECK_LAUNCH("dae_gemm_bf16x3");
   return DAE_OK;
-}
-
-extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
-                               int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
-                               int64_t ldc, int32_t n_store, int32_t special_col, float* special_out, int32_t k_splits,
-                               int32_t accumulate, void* stream) {
-  // 128 x 256 tiles move fewer operand bytes per output, 128 x 128 tiles quantise better onto the 148 SMs: pick the variant
-  // with the smaller (waves x relative tile cost)
-  const int ks = k_splits < 1 ? 1 : k_splits;
-  const int tiles256 = ((M + 127) / 128) * ((N + 255) / 256) * ks, tiles128 = ((M + 127) / 128) * ((N + 127) / 128) * ks;
-  const float cost256 = 2.0f * (float)((tiles256 + 147) / 148), cost128 = 1.1f * (float)((tiles128 + 147) / 148);
-  const int variant = (cost128 < cost256) ? 1 : 0;
-  return gemm_store_dispatch(variant, nullptr, M, N, K, alpha, a_hi, a_lo, lda, a_mn_major, b_hi, b_lo, ldb, b_mn_major, C, ldc,
-                             n_store, special_col, special_out, k_splits, accumulate, stream);
-}
-
-// diagnostic twin of dae_gemm_bf16x3: tile-shape variant + clock64 trace of CTA 0 (trace: int64[1000] device buffer or NULL)
-extern "C" int dae_gemm_bf16x3_tune(int32_t variant, void* trace, int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi,
-                                    const void* a_lo, int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
-                                    int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
-                                    float* special_out, int32_t k_splits, int32_t accumulate, void* stream) {
-  return gemm_store_dispatch(variant, (long long*)trace, M, N, K, alpha, a_hi, a_lo, lda, a_mn_major, b_hi, b_lo, ldb, b_mn_major, C,
-                             ldc, n_store, special_col, special_out, k_splits, accumulate, stream);
 }
 
 extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo, int64_t lde,
@@ -786,7 +832,7 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
   GemmParams p{};
   p.M = Brows; p.N = F; p.K = K; p.k_splits = 1; p.alpha = 1.0f; p.special_col = -1;
   p.indptr = indptr; p.indices = indices; p.values = values; p.rows = rows; p.bv = bv; p.weight = weight; p.stats = stats;
-  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part; p.trace = g_debug_trace;
+  p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part;
   p.tile_ptr = tile_ptr;
   DAE_CUDA(cudaMemsetAsync(row_loss_part, 0, sizeof(float) * Brows, st));
   {

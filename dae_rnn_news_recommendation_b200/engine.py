@@ -101,7 +101,7 @@ class TrainEngine:
 
     def __init__(self, n_features, n_components, enc_act_func='sigmoid', dec_act_func='sigmoid',
                  loss_func='cross_entropy', opt='gradient_descent', learning_rate=0.1, momentum=0.5, alpha=1.0,
-                 triplet_strategy='batch_all', device='cuda:0', process_group=None, gemm=None):
+                 triplet_strategy='batch_all', device='cuda:0', process_group=None, gemm=None, allreduce=None):
         _cabi.lib()  # fail loudly if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _cabi.DaeError('no CUDA device: the DAE hot path has no CPU fallback')
@@ -138,7 +138,7 @@ class TrainEngine:
             self.enc_bwd_mode = 'atomic'
         self._ent_cap = 0
         self.fork_branches = os.environ.get('DAE_FORK', '1') == '1'
-        self._side = None
+        self._sides = [None, None]
         self.Hp = (self.H + 1 + 63) // 64 * 64   # K padding of E / W (+1: the all-ones column that turns dW into [dW | dbv])
         self.Fp = (self.F + 31) // 32 * 32
         self.in_scale = 1.0  # decay noise folds into the encode kernels (utils.decay_noise, autoencoder/utils.py:147-159)
@@ -149,10 +149,11 @@ class TrainEngine:
         self._graph2 = None
         self._ctl_owner = None
         self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
-        # gradient exchange of the data-parallel step: 'nccl' (default) or 'multimem' (in-switch reduction by dae_allreduce_multimem,
-        # captured inside the step's graph; needs NVSwitch multicast)
-        self.allreduce_mode = os.environ.get('DAE_ALLREDUCE', 'nccl') if self.world > 1 else 'none'
-        assert self.allreduce_mode in ('none', 'nccl', 'multimem')
+        # gradient exchange of the data-parallel step: 'nccl' = eager ncclAllReduce between two captured graphs, 'nccl_graph' = the
+        # NCCL all-reduce captured inside the step's graph, 'multimem' = in-switch reduction by dae_allreduce_multimem (a plain
+        # kernel, captured inside the step's graph; needs NVSwitch multicast)
+        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'nccl')) if self.world > 1 else 'none'
+        assert self.allreduce_mode in ('none', 'nccl', 'nccl_graph', 'multimem')
         if self.allreduce_mode == 'multimem':
             self._setup_multimem()
 
@@ -197,10 +198,10 @@ class TrainEngine:
             self.values_c = v(feed.off_values_c, 4 * nnz, torch.float32)
             self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
             if fixed:   # capture the step on this layout (restores the parameters after its warm-up steps)
-                saved = (self._graph, self._graph2)
-                g = self.capture_step_graph(None, B, None, row_stride=0)
+                saved = (self._graph, self._graph2, getattr(self, '_graph_meta', None))
+                g = self.capture_step_graph(None, B, None, row_stride=0, staged=False)
                 self._feed_graph = (key, g, self._graph2)
-                self._graph, self._graph2 = saved
+                self._graph, self._graph2, self._graph_meta = saved
                 self._ctl_owner = None
         if fixed:
             if self._ctl_owner != 'feed':   # cursors: offset 0 / log row 0 never move (stride 0); the optimizer step advances on the device
@@ -265,6 +266,9 @@ class TrainEngine:
         self.labels_b = torch.empty(B, **f32)
         self.seg_lo = torch.empty(B, **i32)
         self.seg_hi = torch.empty(B, **i32)
+        # staged copy of the per-batch buffers (rows, labels, seg_lo, seg_hi, weight, stats): the NEXT batch of a replayed step
+        self._stage = (torch.zeros(B, **i32), torch.zeros(B, **f32), torch.zeros(B, **i32), torch.zeros(B, **i32), torch.zeros(B, **f32),
+                       torch.zeros(STAT_SLOTS, dtype=torch.float64, device=self.device))
         if self.strategy in (1, 2):
             self.S = torch.empty(B, B, **f32)
             self.G = torch.empty(B, B, **f32)
@@ -349,74 +353,174 @@ class TrainEngine:
         self._k('dae_split_bf16', ptr(src), rows, cols, ld_src, ptr(hi), ptr(lo), hi.stride(0), ones_col, float(scale), _stream())
 
     # ---- one training step -----------------------------------------------------------------------------------------
-    def step(self, perm, offset, B, stats_log_row=None, train=True, ctl=None):
+    def _side_stream(self, i):
+        if self._sides[i] is None:
+            self._sides[i] = torch.cuda.Stream(device=self.device)
+        return self._sides[i]
+
+    @staticmethod
+    def _fork(src, dst):
+        """dst waits for everything issued on src so far (an edge of the step's graph once captured)."""
+        ev = torch.cuda.Event()
+        ev.record(src)
+        dst.wait_event(ev)
+
+    def step(self, perm, offset, B, stats_log_row=None, train=True, ctl=None, staged=None):
         """perm: int32 device tensor (epoch permutation) or None (identity); rows perm[offset:offset+B] form the batch.
-        stats_log_row: optional float64[STAT_SLOTS] device view receiving this step's scalars."""
-        F, H, st = self.F, self.H, _stream()
+        stats_log_row: optional float64[STAT_SLOTS] device view receiving this step's scalars.
+        staged = (n_perm, stride): graph-replayed steps of the triplet strategies take their batch from the staging buffers
+        (dae_batch_commit) and stage the batch at cursor + stride for the next replay on a side branch."""
+        F, H = self.F, self.H
         self._ensure_ws(B)
         strat = self.strategy
         self._ctl = ctl  # device int64[4] cursors (offset, log row, optimizer step) when the step is graph-captured
-        self._k('dae_batch_prepare', ptr(perm), int(offset), ptr(ctl), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
-                ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
+        main = torch.cuda.current_stream()
+        st = main.cuda_stream
+        use_stage = staged is not None and strat in (1, 2) and train
+        if use_stage:
+            self._k('dae_batch_commit', B, *[ptr(t) for t in self._stage], ptr(self.rows), ptr(self.labels_b), ptr(self.seg_lo),
+                    ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
+        else:
+            self._k('dae_batch_prepare', ptr(perm), int(offset), ptr(ctl), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
+                    ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
+        self._encode_forward(B, train)
+        self._train_tail(B, strat, self.weight if strat != 0 else None, stats_log_row, train,
+                         stage_next=(perm, staged) if use_stage else None)
+
+    def _stage_next_batch(self, perm, staged, B, stream):
+        n_perm, stride = staged
+        self._k('dae_batch_prepare_next', ptr(perm), int(n_perm), int(stride), ptr(self._ctl), B, ptr(self.labels), self.strategy,
+                *[ptr(t) for t in self._stage], stream.cuda_stream)
+
+    def stage_batch(self, perm, offset, B):
+        """Host-side staging of the batch at `offset` (the first replay after a cursor jump, e.g. an epoch start)."""
+        self._ensure_ws(B)
+        s = self._stage
+        self._k('dae_batch_prepare', ptr(perm), int(offset), None, B, ptr(self.labels), self.strategy, ptr(s[0]), ptr(s[1]), ptr(s[2]),
+                ptr(s[3]), ptr(s[4]), ptr(s[5]), _stream())
+
+    def _encode_forward(self, B, train):
+        """K1 on the batch rows; also emits E as the bf16 hi/lo pair (plus the all-ones column kept in E_hi) the tensor-core GEMMs
+        consume and, for training, the per-column entry counts of the backward gather."""
         cc = self.csr_c
         gather = train and self.enc_bwd_mode == 'gather'
         if gather:
             self._ensure_bucket_scratch(B)
         tc = self.gemm_mode == 'tc'
-        # the kernel also emits E as the bf16 hi/lo pair (plus the all-ones column kept in E_hi) the tensor-core GEMMs consume
-        self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, F, H,
-                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None,
-                ptr(self.E_hi) if tc else None, ptr(self.E_lo) if tc else None, self.Hp, st)
+        self._k('dae_encode_csr_fwd', ptr(cc.indptr), ptr(cc.indices), ptr(self.values_c), ptr(self.rows), B, self.F, self.H,
+                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), self.H, ptr(self.col_count) if gather else None,
+                ptr(self.E_hi) if tc else None, ptr(self.E_lo) if tc else None, self.Hp, _stream())
         if tc:
             self._ensure_w_split()
-        # batch_all: the mining branch (Gram matrix -> triplet sweep -> G + G^T) does not feed the decode branch (the data
-        # weights are closed-form), so the two run as parallel branches (second stream; parallel nodes once graph-captured) and
-        # the short mining CTAs fill the tails of the persistent GEMM kernels.  batch_hard's weights come out of the mining
-        # kernel, so there the order stays sequential.
-        fork = tc and strat == 1 and train and self.fork_branches
+
+    def _train_tail(self, B, strat, weight, stats_log_row, train, stage_next=None, explicit_B=0):
+        """Everything after the encode forward.  Dependencies of the step (tensor-core path):
+
+            K1 -+-> decode(+loss, dZ) -> dE = dZ.W -+-> dE += a(G+G^T)E -> encode backward (dA, dbh, sparse dW) -+-> exchange, optimizer
+                |                                   |                                                          |
+                +-> [mining: S, triplets, G+G^T] ---+        dW = dZ^T.[E|1] (dense dW, dbv) ------------------+
+                +-> zero grad                                 (branch B, starts once dE and dE_tri own the SMs)
+                     [finalize, stage next batch] (tail of the mining branch)
+
+        batch_all's mining needs only E (its data weights are closed-form) and runs as branch A next to the decode chain; the
+        dense dW GEMM only meets the sparse dW of the encode backward in the (zeroed) gradient buffer, where both accumulate, so it
+        runs as branch B next to the latency-bound encode-backward kernels.  batch_hard's weights come out of the mining kernel,
+        so there the mining stays in line.  Eagerly these are streams + events; captured, parallel branches of ONE graph."""
+        F, H = self.F, self.H
+        main = torch.cuda.current_stream()
+        tc = self.gemm_mode == 'tc'
+        gather = train and self.enc_bwd_mode == 'gather'
+        par = tc and train and self.fork_branches                   # branch B exists
+        fork = par and strat == 1                                   # branch A exists
+        rows = self.rows
+        sideA = self._side_stream(0) if (fork or stage_next) else None
+        sideB = self._side_stream(1) if par else None
         if fork:
-            main = torch.cuda.current_stream()
-            if self._side is None:
-                self._side = torch.cuda.Stream(device=self.device)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self._side.wait_event(ev)
-            with torch.cuda.stream(self._side):
+            self._fork(main, sideA)
+            with torch.cuda.stream(sideA):
                 if gather:   # the column-bucket offsets of the backward gather only need the forward kernel's counts
-                    self._k('dae_col_scan', ptr(self.col_count), F, ptr(self.col_start), ptr(self.col_cursor), _stream())
+                    self._k('dae_col_scan', ptr(self.col_count), F, ptr(self.col_start), ptr(self.col_cursor), sideA.cuda_stream)
                     self._scan_done = True
                 self._mining(B, strat, tc)
-                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), _stream())
-                ev2 = torch.cuda.Event()
-                ev2.record(self._side)
-        elif strat != 0:
+                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
+                        sideA.cuda_stream)
+                ev_mined = torch.cuda.Event()
+                ev_mined.record(sideA)
+        elif strat in (1, 2):
             self._mining(B, strat, tc)
-        self._decode_and_backward(B, self.rows, self.weight if strat != 0 else None, train)
+        if par:
+            self._fork(main, sideB)
+            with torch.cuda.stream(sideB):
+                self.grad.zero_()
+                ev_zero = torch.cuda.Event()
+                ev_zero.record(sideB)
+        if stage_next is not None and not fork:   # (batch_hard) the staging buffers were consumed by dae_batch_commit: refill them now
+            self._fork(main, sideA)
+            with torch.cuda.stream(sideA):
+                self._stage_next_batch(stage_next[0], stage_next[1], B, sideA)
+        if not tc:
+            self._decode_and_backward(B, rows, weight, train)
+        else:
+            self._decode_tc(B, rows, weight, train)
+        if not train:
+            self._finalize(B, strat, weight, stats_log_row, main)
+            return
         if fork:
-            # the step's scalars only need the decode row losses (main branch) and the mining statistics (side branch): reduce
-            # them on the side branch while the main one continues with the backward GEMM / encode backward / optimizer
-            ev3 = torch.cuda.Event()
-            ev3.record(torch.cuda.current_stream())
-            self._side.wait_event(ev3)
-            with torch.cuda.stream(self._side):
-                self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(self.weight), B, strat, self.alpha, ptr(self.stats),
-                        ptr(stats_log_row), ptr(ctl), _stream())
-                ev4 = torch.cuda.Event()
-                ev4.record(self._side)
-            self._finalize_done = True
-            torch.cuda.current_stream().wait_event(ev2)
-        if strat != 0 and train:  # dE += alpha (G + G^T) E
+            # the step's scalars only need the decode row losses (main branch) and the mining statistics (branch A): reduce them on
+            # branch A while the main one continues with the backward GEMMs / encode backward / optimizer
+            self._fork(main, sideA)
+            with torch.cuda.stream(sideA):
+                self._finalize(B, strat, weight, stats_log_row, sideA)
+        if tc:
+            Whl, dZhl = (self.W_hi, self.W_lo), (self.dZ_hi, self.dZ_lo)
+            if not par:   # in line: the dense dW is stored first, the encode backward then adds its sparse part
+                self._dW_gemm(B, accumulate=0)
+            # k_splits = -1: stream-K (the 14 tiles of dE / 158 tiles of dW do not fill the 148 SMs in whole waves)
+            self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=-1, tag='gemm_decode_dE')
+        if explicit_B:   # explicit (org, pos, neg) triplets: row-wise softplus(e.e- - e.e+), adds its dE (autoencoder_triplet.py:303-314)
+            E, d, Bx = self.E, self.dE, explicit_B
+            self._k('dae_triplet_explicit', ptr(E[0:Bx]), ptr(E[Bx:2 * Bx]), ptr(E[2 * Bx:3 * Bx]), Bx, H, H, self.alpha, ptr(d[0:Bx]),
+                    ptr(d[Bx:2 * Bx]), ptr(d[2 * Bx:3 * Bx]), ptr(self.stats), main.cuda_stream)
+        if strat in (1, 2):  # dE += alpha (G + G^T) E
+            if fork:
+                main.wait_event(ev_mined)
             if tc:
                 if not fork:
-                    self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0), st)
-                self._tc_gemm(B, H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE, H, accumulate=1,
-                              tag='gemm_dE_tri')
+                    self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
+                            main.cuda_stream)
+                self._tc_gemm(B, H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE, H, k_splits=-1,
+                              accumulate=1, tag='gemm_dE_tri')
             else:
                 self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
                 self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
-        self._encode_backward_and_update(B, self.rows, self.weight if strat != 0 else None, strat, stats_log_row, train)
-        if fork:
-            torch.cuda.current_stream().wait_event(ev4)   # join before the cursors advance / the next step reuses `stats`
+        if par:
+            self._fork(main, sideB)           # branch B: after the zeroing (already on sideB) and after dE / dE_tri were issued
+            with torch.cuda.stream(sideB):
+                self._dW_gemm(B, accumulate=1)
+            main.wait_event(ev_zero)          # the sparse dW / dbh of the encode backward accumulate into the zeroed buffer
+        self._encode_backward(B, rows)
+        if not fork:
+            self._finalize(B, strat, weight, stats_log_row, main)
+        elif stage_next is not None:          # tail of branch A, after the step's scalars
+            with torch.cuda.stream(sideA):
+                self._stage_next_batch(stage_next[0], stage_next[1], B, sideA)
+        if par:
+            self._fork(sideB, main)
+        if sideA is not None and (fork or stage_next is not None):
+            self._fork(sideA, main)           # join before the cursors advance / the next step reuses `stats`
+        if getattr(self, '_defer_update', False):
+            return
+        self._apply_update()
+
+    def _finalize(self, B, strat, weight, stats_log_row, stream):
+        self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(weight), B, strat, self.alpha, ptr(self.stats),
+                ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), stream.cuda_stream)
+
+    def _dW_gemm(self, B, accumulate):
+        """[dW_dec | dbv] = dZ^T . [E | 1]  (F x (H+1): the all-ones column of E_hl delivers dbv)."""
+        self._tc_gemm(self.F, self.H + 1, B, 1.0, (self.dZ_hi, self.dZ_lo), 1, (self.E_hi, self.E_lo), 1, self._gW(), self.H,
+                      n_store=self.H, special_col=self.H, special_out=self._gbv(), k_splits=-1, accumulate=accumulate,
+                      tag='gemm_decode_dW')
 
     def _mining(self, B, strat, tc):
         """S = E.E^T and the triplet kernel (loss, statistics, G = dL/dS; batch_hard: also the data weights)."""
@@ -446,10 +550,9 @@ class TrainEngine:
             self.csr, self.csr_c, self.values_c, self.labels, self.in_scale = saved
 
     def _decode_and_backward(self, B, rows, weight, train=True):
+        """fp32 CUDA-core validation path of the decode chain (gemm_mode 'ffma')."""
         F, H, st = self.F, self.H, _stream()
         c = self.csr
-        if self.gemm_mode == 'tc':
-            return self._decode_and_backward_tc(B, rows, weight, train)
         self._gemm(B, F, H, 1.0, self.E, H, 1, self.W, H, 1, 0.0, self.Z, F, tag='gemm_decode_fwd')  # Z = E.W^T
         self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
                 self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
@@ -459,12 +562,12 @@ class TrainEngine:
         self._gemm(F, H, B, 1.0, self.Z, 1, F, self.E, 1, H, 0.0, self._gW(), H, tag='gemm_decode_dW')  # dW_dec = dZ^T.E
         self._gemm(B, H, F, 1.0, self.Z, F, 1, self.W, 1, H, 0.0, self.dE, H, tag='gemm_decode_dE')    # dE = dZ.W
 
-    def _decode_and_backward_tc(self, B, rows, weight, train=True):
-        """Decode forward + loss + backward on the tensor cores (bf16x3):  Z = E.W^T with the loss epilogue fused
-        (no Z / D / dense X in HBM), dW = dZ^T.[E | 1] (the extra column is dbv), dE = dZ.W (split-K)."""
+    def _decode_tc(self, B, rows, weight, train=True):
+        """Decode forward + loss on the tensor cores (bf16x3):  Z = E.W^T with the loss epilogue fused (no Z / D / dense X in
+        HBM); dZ leaves as the bf16 hi/lo pair the two backward GEMMs consume."""
         F, H, st = self.F, self.H, _stream()
         c = self.csr
-        Ehl, Whl, dZhl = (self.E_hi, self.E_lo), (self.W_hi, self.W_lo), (self.dZ_hi, self.dZ_lo)
+        Ehl, Whl = (self.E_hi, self.E_lo), (self.W_hi, self.W_lo)
         if self.loss != 2:
             self._k('dae_decode_fused_bf16x3', B, F, H, ptr(self.E_hi), ptr(self.E_lo), self.Hp, ptr(self.W_hi), ptr(self.W_lo),
                     self.Hp, ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), ptr(self.bv), self.dec_act, self.loss,
@@ -476,22 +579,12 @@ class TrainEngine:
                     self.dec_act, self.loss, ptr(weight), ptr(self.stats), ptr(self.Z), F, ptr(self.row_loss), st)
             if train:
                 self._tc_split(self.Z, B, F, F, self.dZ_hi, self.dZ_lo)
-        if not train:
-            return
-        # dW_dec (F x H) and dbv (F) in one GEMM: [dW | dbv] = dZ^T . [E | 1]
-        self._tc_gemm(F, H + 1, B, 1.0, dZhl, 1, Ehl, 1, self._gW(), H, n_store=H, special_col=H, special_out=self._gbv(),
-                      tag='gemm_decode_dW')
-        self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=self._dE_splits(B), tag='gemm_decode_dE')
 
-    def _dE_splits(self, B):
-        """split-K factor of dE = dZ.W (K = F): enough work items for ~2 waves of the 148 SMs."""
-        tiles = ((B + 127) // 128) * ((self.H + 255) // 256)
-        return int(max(1, min(round(296.0 / tiles), (self.F + 255) // 256)))
-
-    def _encode_backward_and_update(self, B, rows, weight, strat, stats_log_row, train=True):
+    def _encode_backward(self, B, rows):
+        """K5: dA = dE * f'(A), dbh, and the sparse part of dW (X_c^T . dA) accumulated into the gradient buffer."""
         F, H, st = self.F, self.H, _stream()
         c = self.csr_c
-        if train and self.enc_bwd_mode == 'gather':
+        if self.enc_bwd_mode == 'gather':
             scan_done = getattr(self, '_scan_done', False)
             self._scan_done = False
             self._k('dae_encode_csr_bwd_gather', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
@@ -499,17 +592,9 @@ class TrainEngine:
                     None if scan_done else ptr(self.col_count),
                     ptr(self.col_start), ptr(self.col_cursor), ptr(self.ent_col), ptr(self.ent_row), ptr(self.ent_val), st, n_launch=3,
                     tag='dae_encode_csr_bwd')
-        elif train:
+        else:
             self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
                     ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
-        if getattr(self, '_finalize_done', False):
-            self._finalize_done = False          # already issued on the side branch
-        else:
-            self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(weight), B, strat,
-                    self.alpha, ptr(self.stats), ptr(stats_log_row), ptr(getattr(self, '_ctl', None)), st)
-        if not train or getattr(self, '_defer_update', False):
-            return
-        self._apply_update()
 
     def _setup_multimem(self, n_blocks=148):
         """Move the gradient buffer into symmetric memory bound to a multicast address and create the peer-mapped flag words
@@ -552,30 +637,14 @@ class TrainEngine:
                 ptr(self.W_hi) if tc else None, ptr(self.W_lo) if tc else None, F, H, self.Hp, st)
 
     # ---- explicit (anchor, pos, neg) triplets: DenoisingAutoencoderTriplet ---------------------------------------------
-    def step_explicit(self, perm, offset, B, n_rows_each, stats_log_row=None):
+    def step_explicit(self, perm, offset, B, n_rows_each, stats_log_row=None, ctl=None):
         """self.csr holds [org; pos; neg] stacked (3*n_rows_each rows). autoencoder_triplet.py:256-258,286-288,303-314."""
-        H, st = self.H, _stream()
         B3 = 3 * B
-        self._ctl = None
+        self._ctl = ctl
         self._ensure_ws(B3)
-        idx = perm[offset:offset + B] if perm is not None else torch.arange(offset, offset + B, device=self.device, dtype=torch.int32)
-        self.rows[:B3] = torch.cat([idx, idx + n_rows_each, idx + 2 * n_rows_each])
-        self.stats.zero_()
-        self.stats[STAT['sum_w']] = float(B)  # each of the three reconstruction terms is a mean over B rows
-        c = self.csr_c
-        gather = self.enc_bwd_mode == 'gather'
-        if gather:
-            self._ensure_bucket_scratch(B3)
-        self._k('dae_encode_csr_fwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(self.rows), B3, self.F, H,
-                self.in_scale, ptr(self.W), ptr(self.bh), self.enc_act, ptr(self.E), H, ptr(self.col_count) if gather else None,
-                ptr(self.E_hi) if self.gemm_mode == 'tc' else None, ptr(self.E_lo) if self.gemm_mode == 'tc' else None, self.Hp, st)
-        if self.gemm_mode == 'tc':
-            self._ensure_w_split()
-        self._decode_and_backward(B3, self.rows, None)
-        E, d = self.E, self.dE
-        self._k('dae_triplet_explicit', ptr(E[0:B]), ptr(E[B:2 * B]), ptr(E[2 * B:B3]), B, H, H, self.alpha, ptr(d[0:B]),
-                ptr(d[B:2 * B]), ptr(d[2 * B:B3]), ptr(self.stats), st)
-        self._encode_backward_and_update(B3, self.rows, None, 3, stats_log_row)
+        self._k('dae_batch_prepare_explicit', ptr(perm), int(offset), ptr(ctl), B, int(n_rows_each), ptr(self.rows), ptr(self.stats), _stream())
+        self._encode_forward(B3, True)
+        self._train_tail(B3, 3, None, stats_log_row, True, explicit_B=B)
 
     # ---- transform ------------------------------------------------------------------------------------------------------
     def encode(self, csr, in_scale=1.0, out=None, values=None):
@@ -589,50 +658,64 @@ class TrainEngine:
         return out
 
     # ---- CUDA-graph replay of the step --------------------------------------------------------------------------------
-    def capture_step_graph(self, perm_buf, B, log_buf, row_stride=None):
-        """Capture ONE training step (all kernels, the gradient all-reduce included) into a CUDA graph.  Everything that
+    def capture_step_graph(self, perm_buf, B, log_buf, row_stride=None, staged=True, explicit_n=None):
+        """Capture ONE training step (all kernels, the gradient exchange included) into a CUDA graph.  Everything that
         changes between steps lives in device memory: the batch cursor / log row / optimizer step in `self.ctl`
         (moved by dae_step_advance, the last node of the graph), the permutation in `perm_buf`, the corrupted values in
-        `self.values_c`.  Returns the graph; replay with `graph.replay()` after `set_step_cursor()`."""
+        `self.values_c`.  staged: the triplet strategies take their (label-sorted) batch from staging buffers filled by the
+        previous replay (set_step_cursor stages the first one).  explicit_n: rows per block of the stacked [org; pos; neg] set
+        (DenoisingAutoencoderTriplet).  Returns the graph; replay with `replay_step()` after `set_step_cursor()`."""
         if not hasattr(self, 'ctl'):
             self.ctl = torch.zeros(4, dtype=torch.int64, device=self.device)
         stride = int(B if row_stride is None else row_stride)
         saved = (self.step_count, self.timed)
         self.timed = None
+        n_perm = int(perm_buf.numel()) if perm_buf is not None else 0
+        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and perm_buf is not None
+        self._graph_meta = {'perm': perm_buf, 'B': B, 'staged': use_stage}
+
+        def one_step():
+            if explicit_n is not None:
+                self.step_explicit(perm_buf, 0, B, explicit_n, log_buf, ctl=self.ctl)
+            else:
+                self.step(perm_buf, 0, B, log_buf, ctl=self.ctl, staged=(n_perm, stride) if use_stage else None)
         # warm-up outside capture (workspace allocation, function attributes, NCCL channels)
         snap = (self.theta.clone(), None if self.slot1 is None else self.slot1.clone(), None if self.slot2 is None else self.slot2.clone(),
                 self.ctl.clone())
         self.ctl.copy_(torch.tensor([0, 0, 1, 0], dtype=torch.int64))  # warm-up / capture run on the first rows of perm_buf
+        if use_stage:
+            self.stage_batch(perm_buf, 0, B)
         for _ in range(2):
-            self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+            one_step()
             call('dae_step_advance', ptr(self.ctl), stride, _stream())
         torch.cuda.synchronize(self.device)
         self.theta.copy_(snap[0]); self.ctl.copy_(snap[3])
         if snap[1] is not None: self.slot1.copy_(snap[1])
         if snap[2] is not None: self.slot2.copy_(snap[2])
         self._w_split_valid = False
-        self._ensure_ws(B)
+        self._ensure_ws(3 * B if explicit_n is not None else B)
         if self.gemm_mode == 'tc':
             self._ensure_w_split()
         torch.cuda.synchronize(self.device)
         launches0 = self.launches
-        # world == 1: one graph for the whole step.  world > 1: the NCCL all-reduce stays OUTSIDE the graphs (graph 1 = everything
-        # up to the gradients and the step's scalars, eager all-reduce, graph 2 = optimizer + cursor advance).
+        # world == 1 or an in-graph exchange ('nccl_graph', 'multimem'): one graph for the whole step.  'nccl': the all-reduce stays
+        # OUTSIDE (graph 1 = everything up to the gradients and the step's scalars, eager all-reduce, graph 2 = optimizer + advance).
         g = torch.cuda.CUDAGraph()
         g2 = None
-        if self.world == 1 or self.allreduce_mode == 'multimem':   # the multimem exchange is a plain kernel: it is captured too
-            with torch.cuda.graph(g):
-                self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+        if self.world == 1 or self.allreduce_mode in ('multimem', 'nccl_graph'):
+            # thread_local: NCCL's watchdog thread may query events while this thread captures
+            with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
+                one_step()
                 call('dae_step_advance', ptr(self.ctl), stride, _stream())
         else:
             self._defer_update = True
             try:
-                with torch.cuda.graph(g):
-                    self.step(perm_buf, 0, B, log_buf, ctl=self.ctl)
+                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    one_step()
             finally:
                 self._defer_update = False
             g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
+            with torch.cuda.graph(g2, capture_error_mode='thread_local'):
                 self._apply_update(reduce=False)
                 call('dae_step_advance', ptr(self.ctl), stride, _stream())
         self.graph_launches = self.launches - launches0 + 1   # kernels per replay
@@ -647,6 +730,9 @@ class TrainEngine:
         """Host-side (re)positioning of the device cursors, e.g. at an epoch start."""
         self._ctl_owner = 'fit'
         self.ctl.copy_(torch.tensor([int(offset), int(log_row), self.step_count + 1, 0], dtype=torch.int64), non_blocking=False)
+        m = getattr(self, '_graph_meta', None)
+        if m is not None and m['staged']:      # the replayed step takes its batch from the staging buffers
+            self.stage_batch(m['perm'], int(offset), m['B'])
 
     def replay_step(self):
         self._replay(self._graph, self._graph2)

@@ -85,6 +85,19 @@ int dae_step_advance(int64_t* ctl, int64_t row_stride, void* stream);
 int dae_batch_prepare(const int32_t* perm, int64_t offset, const int64_t* ctl, int32_t B, const float* labels_all,
                       int32_t strategy, int32_t* rows_out, float* labels_out, int32_t* seg_lo,
                       int32_t* seg_hi, float* weight_out, double* stats, void* stream);
+/* The one-CTA sort is 20 us of pure latency, so a graph-replayed step prepares the NEXT batch (cursor ctl[0] + stride) on a side
+ * branch into staging buffers (*_s) while the current step computes -- nothing is written when that batch would run past
+ * n_perm -- and the next step starts with dae_batch_commit, a copy of the staged batch into the live buffers. */
+int dae_batch_prepare_next(const int32_t* perm, int64_t n_perm, int64_t stride, const int64_t* ctl, int32_t B,
+                           const float* labels_all, int32_t strategy, int32_t* rows_s, float* labels_s,
+                           int32_t* seg_lo_s, int32_t* seg_hi_s, float* weight_s, double* stats_s, void* stream);
+int dae_batch_commit(int32_t B, const int32_t* rows_s, const float* labels_s, const int32_t* seg_lo_s,
+                     const int32_t* seg_hi_s, const float* weight_s, const double* stats_s, int32_t* rows,
+                     float* labels_b, int32_t* seg_lo, int32_t* seg_hi, float* weight, double* stats, void* stream);
+/* explicit (org, pos, neg) triplets (autoencoder/utils.py:73-91, autoencoder_triplet.py:106-147): rows_out[3B] = the batch's
+ * rows in the three blocks of the stacked [org; pos; neg] matrix (n_each rows per block); stats zeroed, SUM_W = B. */
+int dae_batch_prepare_explicit(const int32_t* perm, int64_t offset, const int64_t* ctl, int32_t B, int64_t n_each,
+                               int32_t* rows_out, double* stats, void* stream);
 
 /* ---- K1: CSR x dense encode ---------------------------------------------------------------------
  * E[r,:] = f( in_scale * X[rows[r],:] . W + bh ) - f(bh)      (autoencoder.py:377,389; transform :494-497;
@@ -145,7 +158,9 @@ int dae_sgemm(int32_t M, int32_t N, int32_t K, float alpha, const float* A, int6
  * dae_gemm_bf16x3: C[m,n] (+)= alpha * sum_k A(m,k) B(n,k).
  *   a_mn_major = 0: A stored [M x lda] (K contiguous); 1: A stored [K x lda] (M contiguous).  Same for B/N.
  *   columns n < n_store go to C; column special_col (if special_out != NULL) goes to special_out[m].
- *   k_splits > 1 or accumulate != 0: fp32 atomics into C (C is zeroed first unless accumulate).
+ *   k_splits > 1 (uniform split-K), k_splits < 0 (stream-K: the tile x k-block units are shared evenly by the SMs, chosen
+ *   automatically when the 128x256 tiling does not fill whole waves) or accumulate != 0: fp32 atomics into C (C is zeroed
+ *   first unless accumulate).
  * dae_decode_fused_bf16x3: Z = E.W^T with the decode-loss epilogue fused (D = g(Z+bv), CE/MSE row loss
  *   against the clean CSR rows, dZ written directly as bf16 hi/lo [B x ld_dz]); row_loss_part is the
  *   [B] row-loss vector (zeroed here, accumulated with fp32 atomics, one add per half tile).  Replaces autoencoder.py:411 +
@@ -160,18 +175,6 @@ int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_
                     int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
                     int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
                     float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
-/* diagnostic twin of dae_gemm_bf16x3: variant 0 = 128x256 tiles / 2 stages, 1 = 128x128 / 3, 2 = 128x128 / 2;
- * trace = int64[1000] device buffer receiving a clock64 trace of CTA 0 (or NULL) */
-int dae_gemm_bf16x3_tune(int32_t variant, void* trace, int32_t M, int32_t N, int32_t K, float alpha,
-                         const void* a_hi, const void* a_lo, int64_t lda, int32_t a_mn_major,
-                         const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
-                         int64_t ldc, int32_t n_store, int32_t special_col, float* special_out,
-                         int32_t k_splits, int32_t accumulate, void* stream);
-/* diagnostic: subsequent fused-decode launches write a clock64 trace of CTA 0 into trace (int64[1000] device buffer; NULL = off) */
-int dae_debug_set_trace(void* trace);
-/* 128x256-tile launches: 0 = one CTA per tile (default; also env DAE_GEMM_CLUSTER=0), 1 = clusters of two CTAs that share the
- * B tile, each fetching half of it and TMA-multicasting it to both (1/3 less L2->SM operand traffic) */
-int dae_gemm_set_cluster_mode(int32_t mode);
 int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
                             int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
                             const int64_t* indptr, const int32_t* indices, const float* values,

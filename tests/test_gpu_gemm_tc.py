@@ -69,9 +69,32 @@ def test_gemm_split_k_accumulate_and_special_column():
     assert rel_err(C2.cpu().numpy(), 1.0 + want[:, :500]) < 2e-5
 
 
-@pytest.mark.parametrize('loss,dec', [('cross_entropy', 'sigmoid'), ('mean_squared', 'none'), ('mean_squared', 'tanh')])
-def test_fused_decode_matches_unfused(loss, dec):
-    """dae_decode_fused_bf16x3 == dae_sgemm + dae_decode_loss_bwd (the parity-checked CUDA-core path)."""
+@pytest.mark.parametrize('M,N,K,a_mn,b_mn', [(10000, 501, 800, 1, 1), (800, 500, 10000, 0, 1), (300, 700, 2000, 0, 0), (130, 90, 64, 0, 0)])
+def test_gemm_stream_k(M, N, K, a_mn, b_mn):
+    """k_splits = -1: stream-K (the tile x k-block units shared evenly by the SMs) -- the dW / dE shapes of the C2 step, with the
+    [dW | dbv] special column and with accumulation into a non-zero C."""
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=g)
+    B = torch.randn(N, K, device=DEV, generator=g)
+    want = (A.double() @ B.double().t()).cpu().numpy()
+    pad = lambda n: (n + 7) // 8 * 8
+    Aop = _split(A.t().contiguous(), pad(M)) if a_mn else _split(A, pad(K))
+    Bop = _split(B.t().contiguous(), pad(N)) if b_mn else _split(B, pad(K))
+    C = torch.full((M, N - 1), float('nan'), device=DEV)
+    sp = torch.full((M,), float('nan'), device=DEV)
+    _gemm(M, N, K, Aop, a_mn, Bop, b_mn, C, n_store=N - 1, special_col=N - 1, special_out=sp, k_splits=-1)
+    assert rel_err(C.cpu().numpy(), want[:, :N - 1]) < 2e-5
+    assert rel_err(sp.cpu().numpy(), want[:, N - 1]) < 2e-5
+    C2 = torch.ones(M, N, device=DEV)
+    _gemm(M, N, K, Aop, a_mn, Bop, b_mn, C2, k_splits=-1, accumulate=1, alpha=2.0)
+    assert rel_err(C2.cpu().numpy(), 1.0 + 2.0 * want) < 2e-5
+
+
+@pytest.mark.parametrize('loss,dec,zscale', [('cross_entropy', 'sigmoid', 1.0), ('cross_entropy', 'sigmoid', 12.0), ('mean_squared', 'none', 1.0),
+                                             ('mean_squared', 'tanh', 1.0), ('mean_squared', 'sigmoid', 1.0)])
+def test_fused_decode_matches_unfused(loss, dec, zscale):
+    """dae_decode_fused_bf16x3 == dae_sgemm + dae_decode_loss_bwd (the parity-checked CUDA-core path).  zscale = 12 drives many
+    pre-activations past +-10 (the sigmoid/CE fast path must hand those chunks to the exact evaluation); some rows carry weight 0."""
     from dae_rnn_news_recommendation_b200 import _cabi
     from dae_rnn_news_recommendation_b200.engine import DeviceCSR
     B, F, H = 200, 1000, 52
@@ -79,9 +102,10 @@ def test_fused_decode_matches_unfused(loss, dec):
     x = random_csr(B, F, 30, kind='tfidf' if loss != 'cross_entropy' else 'binary', seed=3)
     csr = DeviceCSR(x, DEV)
     E = torch.randn(B, H, device=DEV) * 0.3
-    W = torch.from_numpy(xavier(F, H, 4) * 3).to(DEV)
+    W = torch.from_numpy(xavier(F, H, 4) * 3 * zscale).to(DEV)
     bv = torch.randn(F, device=DEV) * 0.1
     w = torch.rand(B, device=DEV) * 5
+    w[::7] = 0.0
     stats = torch.zeros(16, dtype=torch.float64, device=DEV)
     stats[5] = float(w.sum())
     Z = torch.empty(B, F, device=DEV)
