@@ -31,10 +31,12 @@ class DenoisingAutoencoder(object):
                  dec_act_func='none', loss_func='mean_squared', num_epochs=10, batch_size=10,
                  xavier_init=1, opt='gradient_descent', learning_rate=0.01, momentum=0.5, corr_type='none',
                  corr_frac=0., verbose=True, verbose_step=5, seed=-1, alpha=1, triplet_strategy='batch_all',
-                 device=None, rng_mode='numpy', W_init=None):
+                 device=None, rng_mode='device', W_init=None):
         """Arguments as in the reference (autoencoder.py:20-45).  Extensions: device ('cuda:N'; default: LOCAL_RANK or 0),
-        rng_mode ('numpy' = the reference's host NumPy RNG stream for corruption and shuffling, 'device' = Philox mask +
-        device permutation), W_init (ndarray F x H overriding the Xavier draw)."""
+        rng_mode ('device' = Philox mask + device permutation, the default: an epoch of the UCI config is 3 ms of GPU time, the host
+        RNG alone would take 6 ms; 'numpy' = the reference's host NumPy RNG stream for corruption and shuffling, drawn one epoch
+        ahead on a worker thread -- bit-identical masks and batch order to a seeded reference run), W_init (ndarray F x H
+        overriding the Xavier draw)."""
         self.algo_name = algo_name
         self.model_name = model_name
         self.compress_factor = compress_factor
@@ -150,13 +152,44 @@ class DenoisingAutoencoder(object):
         arr = np.asarray(labels, dtype=np.float32).reshape(-1)  # fed as 'float' (autoencoder.py:352)
         return torch.from_numpy(arr).to(device)
 
-    def _corrupt_on_device(self, train_csr_host, epoch):
+    def _host_rng_prefetch(self, train_csr_host, n):
+        """rng_mode='numpy': the reference's per-epoch draws from the global NumPy stream -- rand(nnz) for the masking noise
+        (utils.py:111), then the shuffle of the row order (utils.py:50-51) -- produced IN THAT ORDER by a worker thread that runs
+        one epoch ahead of the GPU.  Returns a function handing out (keep mask or None, permutation) epoch by epoch."""
+        import queue
+        import threading
+        if self.rng_mode != 'numpy' or self.corr_type not in ('masking', 'none', 'decay'):
+            return None
+        q = queue.Queue(maxsize=2)
+
+        def work():
+            try:
+                for _ in range(self.num_epochs):
+                    keep = utils.masking_keep_mask(train_csr_host, self.corr_frac) if self.corr_type == 'masking' else None
+                    order = list(range(n))
+                    np.random.shuffle(order)
+                    q.put((keep, np.asarray(order, dtype=np.int32)))
+            except BaseException as e:   # noqa: BLE001 -- hand the failure to the consumer instead of dying silently
+                q.put(e)
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+
+        def take():
+            item = q.get()
+            if isinstance(item, BaseException):
+                raise item
+            return item
+        take.thread = t
+        return take
+
+    def _corrupt_on_device(self, train_csr_host, epoch, keep=None):
         """Per-epoch corruption of the WHOLE training set (autoencoder.py:218,248-270)."""
         eng = self.engine
         eng.in_scale = 1.0
         if self.corr_type == 'masking':
             if self.rng_mode == 'numpy':
-                keep = utils.masking_keep_mask(train_csr_host, self.corr_frac)
+                if keep is None:
+                    keep = utils.masking_keep_mask(train_csr_host, self.corr_frac)
                 eng.corrupt_masking(self.corr_frac, keep_host=keep)
             else:
                 eng.corrupt_masking(self.corr_frac, seed=max(self.seed, 0), epoch=epoch)
@@ -198,6 +231,13 @@ class DenoisingAutoencoder(object):
         tail = [s0 for s0 in starts if s0 + bs > n]
         use_graph = (os.environ.get('DAE_CUDA_GRAPH', '1') == '1' and self.corr_type != 'salt_and_pepper' and len(full) >= 2)
         perm_buf = torch.zeros(n, dtype=torch.int32, device=eng.device)
+        if self.triplet_strategy != 'none':   # dae_batch_prepare / the mining kernels hold one batch in shared memory
+            assert bs <= 4096, 'triplet strategies need batch_size <= 4096 rows (got %d)' % bs
+            assert validation_set is None or validation_set.shape[0] <= 4096, \
+                'the validation set is fed as ONE batch (autoencoder.py:300-309): at most 4096 rows with a triplet strategy'
+        if validation_set is not None:        # size the workspaces once: a larger validation batch must not force a re-capture
+            eng._ensure_ws(max(bs, validation_set.shape[0]))
+        prefetch = self._host_rng_prefetch(host_csr, n)
 
         self.history = []  # additive: per-epoch float64 arrays [steps x STAT_SLOTS] of every step's scalars
         i = -1
@@ -207,8 +247,13 @@ class DenoisingAutoencoder(object):
             self.num_triplet_batch = []
             torch.cuda.synchronize(eng.device)
             t0 = time.time()
-            self._corrupt_on_device(host_csr, i)
-            perm_buf.copy_(self._epoch_permutation(n))
+            if prefetch is not None:
+                keep, order = prefetch()
+                self._corrupt_on_device(host_csr, i, keep)
+                perm_buf.copy_(torch.from_numpy(order).to(eng.device, non_blocking=True))
+            else:
+                self._corrupt_on_device(host_csr, i)
+                perm_buf.copy_(self._epoch_permutation(n))
             if world > 1:   # every rank must slice the SAME permutation (also when the run is unseeded)
                 torch.distributed.broadcast(perm_buf, src=0, group=eng.pg)
             if use_graph:
@@ -269,17 +314,32 @@ class DenoisingAutoencoder(object):
             print()
 
     # ------------------------------------------------------------------------------------------------------------------
-    def transform(self, data, name='train', save=False):
-        """Encode `data` with the trained model (reference autoencoder.py:479-505) -> float32 ndarray [N, n_components]."""
+    def transform(self, data, name='train', save=False, shard=False):
+        """Encode `data` with the trained model (reference autoencoder.py:479-505) -> float32 ndarray [N, n_components].
+        shard=True (additive; data-parallel runs): this rank encodes only its contiguous row range `shard_rows(N)` and returns /
+        saves (as `<name>.rank<r>`) that slice -- rows are independent, so there is no collective."""
         if self.engine is None:
             raise _cabi.DaeError('transform() before fit()/load_model()')
         eng = self.engine
+        rows, suffix = None, ''
+        if shard and eng.world > 1:
+            rank = torch.distributed.get_rank(eng.pg)
+            rows = self.shard_rows(data.shape[0], eng.world, rank)
+            suffix = '.rank%d' % rank
+            data = data[rows[0]:rows[1]]          # only the shard travels to the device
+            rows = None
         csr = DeviceCSR(data, eng.device)
-        encoded = eng.encode(csr).cpu().numpy()
+        encoded = eng.encode(csr, rows=rows).cpu().numpy()
         if save:
-            np.save(self.data_dir + name, encoded)
-            np.save(self.data_dir + 'weights', eng.W.cpu().numpy())
+            np.save(self.data_dir + name + suffix, encoded)
+            if not suffix or suffix == '.rank0':
+                np.save(self.data_dir + 'weights', eng.W.cpu().numpy())
         return encoded
+
+    @staticmethod
+    def shard_rows(n, world, rank):
+        """Contiguous row range [lo, hi) of rank `rank` of `world` ranks over n rows (the ranges tile [0, n))."""
+        return (n * rank) // world, (n * (rank + 1)) // world
 
     def load_model(self, shape, model_path):
         """Restore a trained model (reference autoencoder.py:507-527). shape = (n_features, n_components)."""

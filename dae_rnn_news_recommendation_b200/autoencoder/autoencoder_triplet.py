@@ -6,6 +6,7 @@ The reference class crashes on its first batch (self.train_summary is never assi
 a float batch size (utils.py:86-90); this follows the intended maths.  The three matrices are stacked into ONE CSR in
 HBM ([org; pos; neg]) so a step is a single 3B-row pass through the same kernels as the base class.
 """
+import os
 import time
 
 import numpy as np
@@ -63,6 +64,17 @@ class DenoisingAutoencoderTriplet(DenoisingAutoencoder):
         rank = torch.distributed.get_rank(eng.pg) if world > 1 else 0
         starts = utils.shard_batch_starts(n, bs, world, rank)
         log = torch.zeros(max(len(starts), 1), STAT_SLOTS, dtype=torch.float64, device=eng.device)
+        vcsr = None
+        if validation_set is not None:
+            vhost = [canonical_csr(validation_set[k]) for k in keys]
+            vcsr = (DeviceCSR(sp.vstack(vhost).tocsr(), eng.device), vhost[0].shape[0])
+            eng._ensure_ws(3 * max(bs, vcsr[1]))   # size the workspaces once: a larger validation batch must not force a re-capture
+        # Full-size batches are replayed from ONE captured CUDA graph (device-side row ids and cursors); a short last batch and the
+        # salt-and-pepper corruption (its CSR is rebuilt every epoch) run eagerly.
+        full = [s0 for s0 in starts if s0 + bs <= n]
+        tail = [s0 for s0 in starts if s0 + bs > n]
+        use_graph = (os.environ.get('DAE_CUDA_GRAPH', '1') == '1' and self.corr_type != 'salt_and_pepper' and len(full) >= 2)
+        perm_buf = torch.zeros(n, dtype=torch.int32, device=eng.device)
         i = -1
         for i in range(self.num_epochs):
             torch.cuda.synchronize(eng.device)
@@ -81,11 +93,20 @@ class DenoisingAutoencoderTriplet(DenoisingAutoencoder):
                 v = np.round(self.corr_frac * n_features_of(host[0])).astype(int)
                 xc = sp.vstack([utils.salt_and_pepper_noise(h, v) for h in host]).tocsr()
                 eng.set_data(csr, None, None, csr_corrupt=DeviceCSR(xc, eng.device))
-            perm = self._epoch_permutation(n)
+            perm_buf.copy_(self._epoch_permutation(n))
             if world > 1:
-                torch.distributed.broadcast(perm, src=0, group=eng.pg)
-            for k, s in enumerate(starts):
-                eng.step_explicit(perm, s, min(bs, n - s), n, log[k])
+                torch.distributed.broadcast(perm_buf, src=0, group=eng.pg)
+            if use_graph:
+                if eng._graph is None:
+                    eng.capture_step_graph(perm_buf, bs, log, row_stride=bs * world, explicit_n=n)
+                eng.set_step_cursor(full[0], 0)
+                for _ in full:
+                    eng.replay_step()
+                for k, s0 in enumerate(tail):
+                    eng.step_explicit(perm_buf, s0, n - s0, n, log[len(full) + k])
+            else:
+                for k, s0 in enumerate(starts):
+                    eng.step_explicit(perm_buf, s0, min(bs, n - s0), n, log[k])
             torch.cuda.synchronize(eng.device)
             self.train_time = time.time() - t0
             vals = log[:len(starts)].cpu().numpy()
@@ -93,18 +114,33 @@ class DenoisingAutoencoderTriplet(DenoisingAutoencoder):
                                      list(vals[:, STAT['ae_loss']].astype(np.float32)),
                                      list(vals[:, STAT['triplet_loss']].astype(np.float32)))
             if (i + 1) % self.verbose_step == 0:
-                self._print_epoch(i + 1)
+                self._run_validation_error_and_summaries_triplet(i + 1, vcsr)
         else:
             if self.num_epochs != 0 and (i + 1) % self.verbose_step != 0:
-                self._print_epoch(i + 1)
+                self._run_validation_error_and_summaries_triplet(i + 1, vcsr)
 
-    def _print_epoch(self, epoch):
+    def _run_validation_error_and_summaries_triplet(self, epoch, vcsr):
+        """Console lines of the reference (autoencoder_triplet.py:149-199): epoch means of the training scalars, then -- when a
+        validation set was given -- the forward-only cost of the whole (org, pos, neg) validation set, x_corr = x."""
         if self.verbose == 1:
             print('At step %d (%.2f seconds): ' % (epoch, self.train_time), end='')
-            print('[Train Stat (average over past steps)] - Cost: ', end='')
+            print('[Train Stat (average over past steps)] - ', end='')
+            print('Cost: ', end='')
             print('Overall=%.4f\t' % np.mean(self.train_cost_batch[0]), end='')
             print('Autoencoder=%.4f\t' % np.mean(self.train_cost_batch[1]), end='')
-            print('Triplet=%.4f\t' % np.mean(self.train_cost_batch[2]))
+            print('Triplet=%.4f\t' % np.mean(self.train_cost_batch[2]), end='')
+        if vcsr is None:
+            if self.verbose == 1:
+                print()
+            return
+        res = self.engine.evaluate_explicit(vcsr[0], vcsr[1])
+        self.validation_cost = res
+        if self.verbose:
+            print('[Validation Stat (at this step)] - Cost: ', end='')
+            print('Overall=%.4f\t' % res['cost'], end='')
+            print('Autoencoder=%.4f\t' % res['ae_loss'], end='')
+            print('Triplet=%.4f\t' % res['triplet_loss'], end='')
+            print()
 
 
 def n_features_of(m):

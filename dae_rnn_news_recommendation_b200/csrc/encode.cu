@@ -135,6 +135,117 @@ __global__ void __launch_bounds__(kEncThreads * G) encode_fwd_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// transform-sized K1: persistent CTAs that keep the HOT rows of W in shared memory.
+//
+// Word frequencies are Zipfian: a few hundred columns carry about half of all stored entries.  The row-gather kernel above pulls
+// every W row (2 kB at H = 500) through L2 -> L1 for every entry -- 20 GB per 100 k articles, 66x the algorithmic bytes, and the
+// L2 -> L1 fill path is what it saturates.  Here each CTA (one per SM, 4 row groups of 128 threads) first stages the K most frequent
+// rows of W into its shared memory with 1-D bulk-TMA copies (cp.async.bulk, one contiguous W row per copy, completion on an
+// mbarrier) and then serves entries of those columns from shared memory; only the cold tail still gathers from L2.
+// hot_slot[col] = slot of the column in the staged set, or -1.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kHotGroups = 4;
+
+__device__ __forceinline__ uint32_t enc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int ACT, int NC>
+__global__ void __launch_bounds__(kEncThreads * kHotGroups, 1) encode_fwd_hot_kernel(
+    const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values, int n_rows, int H,
+    float in_scale, const float* __restrict__ W, const float* __restrict__ bh, float* __restrict__ E, int64_t ldE,
+    const int32_t* __restrict__ hot_cols, const int32_t* __restrict__ hot_slot, int K) {
+  extern __shared__ __align__(16) uint8_t enc_smem[];
+  float* s_w = reinterpret_cast<float*>(enc_smem);                       // [K][H] staged rows of W
+  __shared__ int s_col[kHotGroups][kEncThreads];
+  __shared__ int s_slot[kHotGroups][kEncThreads];
+  __shared__ float s_val[kHotGroups][kEncThreads];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int tid = threadIdx.x, grp = tid / kEncThreads, gt = tid % kEncThreads;
+  const uint32_t bar = enc_smem_u32(&s_bar);
+  const uint32_t row_bytes = (uint32_t)H * 4u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)K) : "memory");
+  __syncthreads();
+  for (int k = tid; k < K; k += blockDim.x) {   // one bulk copy per hot row: 2 kB contiguous in W, contiguous in shared memory
+    const float* src = W + (int64_t)hot_cols[k] * H;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(enc_smem_u32(s_w + (int64_t)k * H)),
+                 "l"(src), "r"(row_bytes), "r"(bar)
+                 : "memory");
+  }
+  {  // everybody waits for the staged rows (phase 0 of the barrier)
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(ok)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  int hcol[NC];
+  float fb[NC][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    hcol[c] = (gt + c * kEncThreads) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) fb[c][e] = (hcol[c] < H) ? __ldg(bh + hcol[c] + e) : 0.0f;
+  }
+  for (int r = blockIdx.x * kHotGroups + grp; r < n_rows; r += gridDim.x * kHotGroups) {
+    const int64_t p0 = indptr[r], p1 = indptr[r + 1];
+    float acc[NC][4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[c][e] = 0.0f;
+    for (int64_t base = p0; base < p1; base += kEncThreads) {
+      const int64_t p = base + gt;
+      int col = 0, slot = -1;
+      float v = 0.0f;
+      if (p < p1) { col = __ldg(indices + p); v = __ldg(values + p) * in_scale; slot = __ldg(hot_slot + col); }
+      s_col[grp][gt] = col; s_slot[grp][gt] = slot; s_val[grp][gt] = v;
+      asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kEncThreads) : "memory");   // the group's 128 threads
+      const int cnt = (int)((p1 - base < (int64_t)kEncThreads) ? (p1 - base) : (int64_t)kEncThreads);
+#pragma unroll 8
+      for (int q = 0; q < cnt; ++q) {
+        const float vq = s_val[grp][q];
+        const int sq = s_slot[grp][q];                 // uniform over the group: no divergence
+        const float* wg = W + (int64_t)s_col[grp][q] * H;
+        const float* ws = s_w + (int64_t)(sq < 0 ? 0 : sq) * H;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          if (hcol[c] < H) {
+            float4 w;
+            if (sq >= 0) w = *reinterpret_cast<const float4*>(ws + hcol[c]);
+            else w = __ldg(reinterpret_cast<const float4*>(wg + hcol[c]));
+            acc[c][0] = fmaf(vq, w.x, acc[c][0]); acc[c][1] = fmaf(vq, w.y, acc[c][1]);
+            acc[c][2] = fmaf(vq, w.z, acc[c][2]); acc[c][3] = fmaf(vq, w.w, acc[c][3]);
+          }
+        }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kEncThreads) : "memory");
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (hcol[c] < H) {
+        float4 o;
+        o.x = act_fwd<ACT>(acc[c][0] + fb[c][0]) - act_fwd<ACT>(fb[c][0]);
+        o.y = act_fwd<ACT>(acc[c][1] + fb[c][1]) - act_fwd<ACT>(fb[c][1]);
+        o.z = act_fwd<ACT>(acc[c][2] + fb[c][2]) - act_fwd<ACT>(fb[c][2]);
+        o.w = act_fwd<ACT>(acc[c][3] + fb[c][3]) - act_fwd<ACT>(fb[c][3]);
+        *reinterpret_cast<float4*>(E + (int64_t)r * ldE + hcol[c]) = o;
+      }
+    }
+  }
+}
+
 // backward: dA = dE * f'(A) (A recovered from E + f(bh)), dbh += dA - f'(bh) dE, dW[col,:] += val * dA
 template <int ACT, int VW, int NC>
 __global__ void __launch_bounds__(kEncThreads) encode_bwd_kernel(
@@ -495,5 +606,34 @@ extern "C" int dae_col_scan(const int32_t* col_count, int32_t F, int32_t* col_st
   DAE_REQUIRE(col_count && col_start && col_cursor && F > 0, "dae_col_scan: bad arguments");
   col_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(col_count, F, col_start, col_cursor);
   DAE_CHECK_LAUNCH("dae_col_scan");
+  return DAE_OK;
+}
+
+extern "C" int dae_encode_csr_fwd_hot(const int64_t* indptr, const int32_t* indices, const float* values, int32_t n_rows, int32_t F,
+                                      int32_t H, float in_scale, const float* W, const float* bh, int32_t enc_act, float* E, int64_t ldE,
+                                      const int32_t* hot_cols, const int32_t* hot_slot, int32_t K, void* stream) {
+  using namespace dae;
+  DAE_REQUIRE(indptr && indices && values && W && bh && E && hot_cols && hot_slot, "dae_encode_csr_fwd_hot: null pointer");
+  DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H && K >= 1, "dae_encode_csr_fwd_hot: bad shape");
+  DAE_REQUIRE(H % 4 == 0 && ldE % 4 == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)E & 15) == 0 && H <= 8 * kEncThreads,
+              "dae_encode_csr_fwd_hot: needs H %% 4 == 0, H <= 1024 and 16-byte aligned W / E (use dae_encode_csr_fwd otherwise)");
+  const size_t smem = (size_t)K * H * 4;
+  DAE_REQUIRE(smem <= 200 * 1024, "dae_encode_csr_fwd_hot: K * H * 4 = %zu bytes of staged rows exceed 200 KB", smem);
+  if (n_rows == 0) return DAE_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  DAE_CUDA(cudaGetDevice(&dev));
+  DAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nc = (H + 4 * kEncThreads - 1) / (4 * kEncThreads);
+  const int grid = (n_rows + kHotGroups - 1) / kHotGroups < sms ? (n_rows + kHotGroups - 1) / kHotGroups : sms;
+#define DAE_HOT(ACT, NC)                                                                                                          \
+  do {                                                                                                                            \
+    auto kern = encode_fwd_hot_kernel<ACT, NC>;                                                                                   \
+    DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                                \
+    kern<<<grid, kEncThreads * kHotGroups, smem, st>>>(indptr, indices, values, n_rows, H, in_scale, W, bh, E, ldE, hot_cols, hot_slot, K); \
+  } while (0)
+  DAE_DISPATCH_ACT(enc_act, ACT, { if (nc <= 1) DAE_HOT(ACT, 1); else DAE_HOT(ACT, 2); });
+#undef DAE_HOT
+  DAE_CHECK_LAUNCH("dae_encode_csr_fwd_hot");
   return DAE_OK;
 }

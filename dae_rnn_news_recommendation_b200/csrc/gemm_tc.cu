@@ -23,7 +23,6 @@ namespace dae {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kTcThreads = 256;
 constexpr int kAccStages = 2;
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -75,6 +74,62 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster, on the two SMs of one TPC, work on ONE 256-row UMMA tile.  Each CTA
+// loads its own 128 rows of A and HALF of the B tile (the tensor cores read the other half from the peer's shared memory), so a
+// k-block costs each SM 64 KB of L2 -> SM traffic instead of 96 KB.  Only the even ("leader") CTA issues MMAs.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: "the same offset in the leader CTA"
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of a CTA pair: lands in THIS CTA's shared memory, completes its bytes on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit that arrives on the mbarrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)0x3)
+               : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > 4096u) { __nanosleep(64); if (spins > (1u << 26)) __trap(); }
+  }
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -118,12 +173,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-__host__ __device__ constexpr uint32_t make_idesc(int block_n, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int block_n, bool a_mn, bool b_mn, int umma_m = BLOCK_M) {
   return (1u << 4)                       // D format f32
          | (1u << 7) | (1u << 10)        // A, B = bf16
          | ((a_mn ? 1u : 0u) << 15)      // A major: 0 = K, 1 = MN
          | ((b_mn ? 1u : 0u) << 16)      // B major
-         | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+         | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -161,19 +216,23 @@ constexpr int tc_threads(int ew) { return 128 + 32 * ew; }  // warps 0-3: TMA / 
 //             tile, whole tiles, and the head of another -- every segment is one accumulator pass + one (atomic) epilogue.
 //             Balances shapes whose tile count does not fill the 148 SMs evenly (dW: 158 tiles) without shrinking the tiles.
 struct Sched {
-  int tiles_m, tiles, kb_total, kb_per_split, n_work, stream, w;
+  int tiles_m, tiles, kb_total, kb_per_split, n_work, stream, w, n_cta;
   long long u, u_end;
-  __device__ __forceinline__ void init(const GemmParams& p, int block_n) {
+  // pair != 0: the two CTAs of a cluster walk the SAME list; an m index then names a pair of 128-row tiles
+  __device__ __forceinline__ void init(const GemmParams& p, int block_n, int pair = 0) {
+    const int cta = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    n_cta = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    if (pair) tiles_m = (tiles_m + 1) / 2;
     tiles = tiles_m * ((p.N + block_n - 1) / block_n);
     kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
     stream = p.stream_k;
     kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
     n_work = tiles * p.k_splits;
-    w = blockIdx.x;
+    w = cta;
     const long long U = (long long)tiles * kb_total;
-    u = (long long)blockIdx.x * U / gridDim.x;
-    u_end = (long long)(blockIdx.x + 1) * U / gridDim.x;
+    u = (long long)cta * U / n_cta;
+    u_end = (long long)(cta + 1) * U / n_cta;
   }
   __device__ __forceinline__ bool next(int& mb, int& nb, int& kb0, int& kb1) {
     int tile;
@@ -189,7 +248,7 @@ struct Sched {
       tile = w % tiles;
       kb0 = (w / tiles) * kb_per_split;
       kb1 = min(kb_total, kb0 + kb_per_split);
-      w += gridDim.x;
+      w += n_cta;
     }
     mb = tile % tiles_m;
     nb = tile / tiles_m;
@@ -295,14 +354,16 @@ __device__ __forceinline__ bool decode_chunk_sigmoid_ce(const uint32_t (&r)[16],
   return ok;
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
+// PAIR = 1: cta_group::2 (see the PTX wrappers above); BLOCK_N is then the pair tile's N, of which each CTA stages BLOCK_N / 2.
+template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS, int PAIR>
 __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore), 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
                                                                       const __grid_constant__ CUtensorMap tm_a_lo,
                                                                       const __grid_constant__ CUtensorMap tm_b_hi,
                                                                       const __grid_constant__ CUtensorMap tm_b_lo,
                                                                       const GemmParams p) {
   constexpr int A_TILE = BLOCK_M * BLOCK_K * 2;   // bytes of one bf16 A tile (16 KB)
-  constexpr int B_TILE = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;   // n rows of the B tile staged by this CTA
+  constexpr int B_TILE = B_ROWS * BLOCK_K * 2;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
   constexpr int kEpiWarps = (EPI == EPI_DECODE) ? kEwDecode : kEwStore;
   constexpr int kParts = kEpiWarps / 4;          // column parts per tile (one per epilogue warp of a lane quarter)
@@ -319,22 +380,29 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Sched sched;
-  sched.init(p, BLOCK_N);
+  sched.init(p, BLOCK_N, PAIR);
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs), 1 = peer
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiWarps); }
+    // PAIR: the leader's accumulator-free barrier collects the epilogue warps of BOTH CTAs
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -350,25 +418,52 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
           uint8_t* sa_lo = sa_hi + A_TILE;
           uint8_t* sb_hi = sa_lo + A_TILE;
           uint8_t* sb_lo = sb_hi + B_TILE;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (!p.a_mn) {
-            tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi, kb * BLOCK_K, mb * BLOCK_M);
-            tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo, kb * BLOCK_K, mb * BLOCK_M);
-          } else {
+          const int mt = PAIR ? mb * 2 + (int)crank : mb;            // this CTA's 128-row m tile
+          const int n_base = nb * BLOCK_N + (PAIR ? (int)crank * B_ROWS : 0);
+          if (!PAIR) {
+            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi, kb * BLOCK_K, mt * BLOCK_M);
+              tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo, kb * BLOCK_K, mt * BLOCK_M);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j) {
-              tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi + j * 8192, mb * BLOCK_M + j * 64, kb * BLOCK_K);
-              tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mb * BLOCK_M + j * 64, kb * BLOCK_K);
+              for (int j = 0; j < BLOCK_M / 64; ++j) {
+                tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi + j * 8192, mt * BLOCK_M + j * 64, kb * BLOCK_K);
+                tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mt * BLOCK_M + j * 64, kb * BLOCK_K);
+              }
             }
-          }
-          if (!p.b_mn) {
-            tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, nb * BLOCK_N);
-            tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, nb * BLOCK_N);
-          } else {
+            if (!p.b_mn) {
+              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, n_base);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, n_base);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j) {
-              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
-              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, nb * BLOCK_N + j * 64, kb * BLOCK_K);
+              for (int j = 0; j < B_ROWS / 64; ++j) {
+                tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, n_base + j * 64, kb * BLOCK_K);
+                tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, n_base + j * 64, kb * BLOCK_K);
+              }
+            }
+          } else {
+            // the LEADER's full barrier counts the bytes of both CTAs; the peer only issues its loads (which complete there)
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d_2sm(&tm_a_hi, &full_bar[stage], sa_hi, kb * BLOCK_K, mt * BLOCK_M);
+              tma_load_2d_2sm(&tm_a_lo, &full_bar[stage], sa_lo, kb * BLOCK_K, mt * BLOCK_M);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j) {
+                tma_load_2d_2sm(&tm_a_hi, &full_bar[stage], sa_hi + j * 8192, mt * BLOCK_M + j * 64, kb * BLOCK_K);
+                tma_load_2d_2sm(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mt * BLOCK_M + j * 64, kb * BLOCK_K);
+              }
+            }
+            if (!p.b_mn) {
+              tma_load_2d_2sm(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, n_base);
+              tma_load_2d_2sm(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, n_base);
+            } else {
+#pragma unroll
+              for (int j = 0; j < B_ROWS / 64; ++j) {
+                tma_load_2d_2sm(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, n_base + j * 64, kb * BLOCK_K);
+                tma_load_2d_2sm(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, n_base + j * 64, kb * BLOCK_K);
+              }
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -377,13 +472,14 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0, PAIR ? 2 * BLOCK_M : BLOCK_M);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int mb, nb, kb0, kb1;
       while (sched.next(mb, nb, kb0, kb1)) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
+        if (PAIR) mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);   // the epilogues of both CTAs have drained this stage
+        else mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);                // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -400,12 +496,23 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
             const uint64_t db_hi = make_desc(sb_hi + k * b_step, b_lbo, 1024);
             const uint64_t db_lo = make_desc(sb_lo + k * b_step, b_lbo, 1024);
             const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
-            umma_bf16(tmem_d, da_lo, db_hi, idesc, first);   // small terms first
-            umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
-            umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
+            if (PAIR) {
+              umma_bf16_2sm(tmem_d, da_lo, db_hi, idesc, first);
+              umma_bf16_2sm(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_bf16_2sm(tmem_d, da_hi, db_hi, idesc, 1u);
+            } else {
+              umma_bf16(tmem_d, da_lo, db_hi, idesc, first);   // small terms first
+              umma_bf16(tmem_d, da_hi, db_lo, idesc, 1u);
+              umma_bf16(tmem_d, da_hi, db_hi, idesc, 1u);
+            }
           }
-          umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          if (PAIR) {                            // both CTAs' producers / epilogues are released
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_2sm(&tmem_full_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
+            if (kb == kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -421,6 +528,7 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
     int acc = 0; uint32_t acc_phase = 0;
     int mb, nb, kb0, kb1;
     while (sched.next(mb, nb, kb0, kb1)) {
+      if (PAIR) mb = mb * 2 + (int)crank;     // this CTA's 128-row m tile of the pair
       const int m = mb * BLOCK_M + row_in_tile;
       const int n0 = nb * BLOCK_N + half * HALF_N;
       if (EPI == EPI_DECODE) {  // stage this tile's visible-bias slice (named barrier 1: the epilogue threads)
@@ -581,16 +689,17 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) { if (PAIR) mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else mbar_arrive(&tmem_empty_bar[acc]); }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer may still read this CTA's tiles / signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
@@ -708,10 +817,13 @@ static int sm_count() {
   return n[dev];
 }
 
-template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS>
+static int g_pair_mode = -1;   // -1: by size (dae_gemm_config); 0: never; 1: whenever the shape allows
+
+template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS, int PAIR>
 static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStream_t st) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
+  constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;
   // K-major: tensor [rows=MN x cols=K], box {64 k, tile rows};  MN-major: tensor [rows=K x cols=MN], box {64 mn, 64 k}
   if (!A.mn_major) {
     if ((rc = make_map(&ta_hi, A.hi, p.K, p.M, A.ld, BLOCK_M))) return rc;
@@ -721,33 +833,52 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
     if ((rc = make_map(&ta_lo, A.lo, p.M, p.K, A.ld, 64))) return rc;
   }
   if (!B.mn_major) {
-    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, BLOCK_N))) return rc;
-    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, BLOCK_N))) return rc;
+    if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, B_ROWS))) return rc;
+    if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, B_ROWS))) return rc;
   } else {
     if ((rc = make_map(&tb_hi, B.hi, p.N, p.K, B.ld, 64))) return rc;
     if ((rc = make_map(&tb_lo, B.lo, p.N, p.K, B.ld, 64))) return rc;
   }
   p.a_mn = A.mn_major; p.b_mn = B.mn_major;
-  constexpr int smem = STAGES * (2 * BLOCK_M * BLOCK_K * 2 + 2 * BLOCK_N * BLOCK_K * 2) + 1024;
+  constexpr int smem = STAGES * (2 * BLOCK_M * BLOCK_K * 2 + 2 * B_ROWS * BLOCK_K * 2) + 1024;
   constexpr int threads = tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore);
-  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  if (PAIR) tiles_m = (tiles_m + 1) / 2;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int kblocks = (p.K + BLOCK_K - 1) / BLOCK_K;
-  auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS>;
+  auto kern = gemm_bf16x3_kernel<BLOCK_N, STAGES, EPI, ACT, LOSS, PAIR>;
   static bool attr_done[64] = {false};
   if ((rc = ensure_smem_attr(kern, smem, attr_done))) return rc;
-  const int sms = sm_count();
-  int grid;
+  const int slots = PAIR ? sm_count() / 2 : sm_count();   // CTAs, or CTA pairs, resident at once
+  int n;
   if (p.stream_k) {   // segments of at least ~6 k-blocks: a shorter main loop does not amortise its (atomic) epilogue
     const long long units = (long long)tiles_m * tiles_n * kblocks;
     long long g = units / 6;
     if (g < 1) g = 1;
-    grid = (int)(g < sms ? g : sms);
+    n = (int)(g < slots ? g : slots);
   } else {
     const int items = tiles_m * tiles_n * p.k_splits;
-    grid = items < sms ? items : sms;
+    n = items < slots ? items : slots;
   }
-  kern<<<grid, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  if (!PAIR) {
+    kern<<<n, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    DAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  }
   return DAE_OK;
+}
+
+// CTA pairs pay off once the GEMM is large enough to be bound by L2 -> SM operand traffic (>= ~2 GFLOP here: decode, dW, dE)
+static bool use_pair(int M, int N, int K) {
+  if (g_pair_mode == 0) return false;
+  if (g_pair_mode == 1) return true;
+  return (double)M * (double)N * (double)K >= 1.0e9 && M > 128;
 }
 
 }  // namespace dae
@@ -772,6 +903,9 @@ extern "C" int dae_sym_split_bf16(const float* G, int32_t B, int64_t ldg, float 
   DAE_CHECK_LAUNCH("dae_sym_split_bf16");
   return DAE_OK;
 }
+
+// test hook: -1 = CTA pairs (cta_group::2) for the large GEMMs only (default), 0 = never, 1 = always
+extern "C" int dae_gemm_config(int32_t pair_mode) { dae::g_pair_mode = pair_mode < 0 ? -1 : (pair_mode ? 1 : 0); return DAE_OK; }
 
 extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
                                int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
@@ -812,8 +946,9 @@ extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, con
   int rc;
   const int tiles256 = tm * tn256 * k_splits, tiles128 = tm * tn128 * k_splits;
   const float cost256 = 2.0f * (float)((tiles256 + sms - 1) / sms), cost128 = 1.1f * (float)((tiles128 + sms - 1) / sms);
-  if (!stream_k && cost128 < cost256) rc = launch_gemm<128, 3, EPI_STORE, 0, 0>(A, B, p, st);
-  else rc = launch_gemm<256, 2, EPI_STORE, 0, 0>(A, B, p, st);
+  if (use_pair(M, N, K)) rc = launch_gemm<256, 3, EPI_STORE, 0, 0, 1>(A, B, p, st);
+  else if (!stream_k && cost128 < cost256) rc = launch_gemm<128, 3, EPI_STORE, 0, 0, 0>(A, B, p, st);
+  else rc = launch_gemm<256, 2, EPI_STORE, 0, 0, 0>(A, B, p, st);
   if (rc) return rc;
   DAE_CHECK_LAUNCH("dae_gemm_bf16x3");
   return DAE_OK;
@@ -842,7 +977,8 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
   }
   Operand A{e_hi, e_lo, lde, 0}, B{w_hi, w_lo, ldw, 0};
   int rc = 0;
-#define DAE_DEC(ACT, LOSS) rc = launch_gemm<256, 2, EPI_DECODE, ACT, LOSS>(A, B, p, st)
+  const bool pair = use_pair(Brows, F, K);
+#define DAE_DEC(ACT, LOSS) rc = pair ? launch_gemm<256, 3, EPI_DECODE, ACT, LOSS, 1>(A, B, p, st) : launch_gemm<256, 2, EPI_DECODE, ACT, LOSS, 0>(A, B, p, st)
   if (loss_func == DAE_LOSS_CE) {
     if (dec_act == DAE_ACT_SIGMOID) DAE_DEC(DAE_ACT_SIGMOID, DAE_LOSS_CE);
     else if (dec_act == DAE_ACT_TANH) DAE_DEC(DAE_ACT_TANH, DAE_LOSS_CE);

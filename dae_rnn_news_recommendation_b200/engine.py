@@ -463,6 +463,10 @@ class TrainEngine:
         else:
             self._decode_tc(B, rows, weight, train)
         if not train:
+            if explicit_B:   # forward only: the kernel's loss statistics are what is wanted, its dE contribution lands in scratch
+                E, d, Bx = self.E, self.dE, explicit_B
+                self._k('dae_triplet_explicit', ptr(E[0:Bx]), ptr(E[Bx:2 * Bx]), ptr(E[2 * Bx:3 * Bx]), Bx, H, H, self.alpha, ptr(d[0:Bx]),
+                        ptr(d[Bx:2 * Bx]), ptr(d[2 * Bx:3 * Bx]), ptr(self.stats), main.cuda_stream)
             self._finalize(B, strat, weight, stats_log_row, main)
             return
         if fork:
@@ -545,6 +549,23 @@ class TrainEngine:
             self.set_data(csr, None, labels)
             self.in_scale = 1.0
             self.step(None, 0, csr.shape[0] if B is None else B, None, train=False)
+            return self.read_stats()
+        finally:
+            self.csr, self.csr_c, self.values_c, self.labels, self.in_scale = saved
+
+    def evaluate_explicit(self, csr_stacked, n_each):
+        """Forward-only cost of a stacked [org; pos; neg] set fed as ONE batch with x_corr = x: the validation pass of
+        DenoisingAutoencoderTriplet (reference autoencoder/autoencoder_triplet.py:166-199).  Returns the stats dict."""
+        saved = (self.csr, self.csr_c, self.values_c, self.labels, self.in_scale)
+        try:
+            self.set_data(csr_stacked, None, None)
+            self.in_scale = 1.0
+            B = int(n_each)
+            self._ctl = None
+            self._ensure_ws(3 * B)
+            self._k('dae_batch_prepare_explicit', None, 0, None, B, B, ptr(self.rows), ptr(self.stats), _stream())
+            self._encode_forward(3 * B, False)
+            self._train_tail(3 * B, 3, None, None, False, explicit_B=B)
             return self.read_stats()
         finally:
             self.csr, self.csr_c, self.values_c, self.labels, self.in_scale = saved
@@ -647,14 +668,40 @@ class TrainEngine:
         self._train_tail(B3, 3, None, stats_log_row, True, explicit_B=B)
 
     # ---- transform ------------------------------------------------------------------------------------------------------
-    def encode(self, csr, in_scale=1.0, out=None, values=None):
-        """E = f(in_scale * X.W + bh) - f(bh) for every row of csr (autoencoder.py:479-505)."""
-        N = csr.shape[0]
+    HOT_MIN_ROWS = 16384   # below this the per-launch staging of the hot rows (200 KB per SM) does not pay
+
+    def _hot_columns(self, csr):
+        """The K most frequent feature columns of `csr` (K rows of W fit 200 KB of shared memory) and the column -> slot table
+        of dae_encode_csr_fwd_hot.  One histogram pass over the column ids; cached on the matrix."""
+        hot = getattr(csr, '_hot', None)
+        K = min(self.F, (200 * 1024) // (self.H * 4))
+        if hot is None or hot[2] != K:
+            counts = torch.bincount(csr.indices, minlength=self.F)
+            cols = torch.topk(counts, K).indices.to(torch.int32)
+            slot = torch.full((self.F,), -1, dtype=torch.int32, device=self.device)
+            slot[cols.long()] = torch.arange(K, dtype=torch.int32, device=self.device)
+            hot = (cols.contiguous(), slot, K)
+            csr._hot = hot
+        return hot
+
+    def encode(self, csr, in_scale=1.0, out=None, values=None, rows=None):
+        """E = f(in_scale * X.W + bh) - f(bh) for every row of csr (autoencoder.py:479-505).  rows = (lo, hi): only that row range
+        (a rank's shard of a data-parallel transform: no collective, each rank writes its slice of E)."""
+        lo, hi = (0, csr.shape[0]) if rows is None else (int(rows[0]), int(rows[1]))
+        N = hi - lo
         if out is None:
             out = torch.empty(N, self.H, dtype=torch.float32, device=self.device)
-        self._k('dae_encode_csr_fwd', ptr(csr.indptr), ptr(csr.indices), ptr(csr.values if values is None else values), None,
-                N, self.F, self.H, float(in_scale), ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, None, None, None, 0, _stream(),
-                tag='encode_transform')
+        if N == 0:
+            return out
+        indptr = csr.indptr[lo:hi + 1]      # absolute offsets into indices / values: a row range is just a window of indptr
+        vals = csr.values if values is None else values
+        if N >= self.HOT_MIN_ROWS and self.H % 4 == 0 and self.H <= 1024:
+            cols, slot, K = self._hot_columns(csr)
+            self._k('dae_encode_csr_fwd_hot', ptr(indptr), ptr(csr.indices), ptr(vals), N, self.F, self.H, float(in_scale), ptr(self.W),
+                    ptr(self.bh), self.enc_act, ptr(out), self.H, ptr(cols), ptr(slot), K, _stream(), tag='encode_transform')
+        else:
+            self._k('dae_encode_csr_fwd', ptr(indptr), ptr(csr.indices), ptr(vals), None, N, self.F, self.H, float(in_scale),
+                    ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, None, None, None, 0, _stream(), tag='encode_transform')
         return out
 
     # ---- CUDA-graph replay of the step --------------------------------------------------------------------------------

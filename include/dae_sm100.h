@@ -138,6 +138,15 @@ int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* indices, con
                               float* dbh, const int32_t* col_count, int32_t* col_start, int32_t* col_cursor,
                               int32_t* ent_col, int32_t* ent_row, float* ent_val, void* stream);
 
+/* transform-sized K1 (many rows, one launch): persistent CTAs stage the K most frequent rows of W (hot_cols[K], 2 kB each at
+ * H = 500) in shared memory with 1-D bulk-TMA copies and serve the entries of those columns from there; the cold tail gathers from
+ * L2 as in dae_encode_csr_fwd.  hot_slot[F] = index of the column in hot_cols, or -1.  K * H * 4 <= 200 KB, H % 4 == 0.
+ * Same results as dae_encode_csr_fwd up to fp32 summation order inside a row (identical: entries are added in CSR order). */
+int dae_encode_csr_fwd_hot(const int64_t* indptr, const int32_t* indices, const float* values, int32_t n_rows,
+                           int32_t F, int32_t H, float in_scale, const float* W, const float* bh, int32_t enc_act,
+                           float* E, int64_t ldE, const int32_t* hot_cols, const int32_t* hot_slot, int32_t K,
+                           void* stream);
+
 /* ---- fp32 reference GEMM (CUDA cores) ----------------------------------------------------------
  * C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + beta * C[m,n]; generic strides.
  * The v1 / validation path for the dense contractions (autoencoder.py:411 and its autodiff,
@@ -175,6 +184,9 @@ int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_
                     int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
                     int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
                     float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
+/* Tile engine selection of the two entry points above (test hook): -1 = CTA pairs (cta_group::2: two SMs share one 256-row UMMA
+ * tile, each staging half of the B operand) for the large GEMMs only -- the default --, 0 = never, 1 = whenever possible. */
+int dae_gemm_config(int32_t pair_mode);
 int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
                             int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
                             const int64_t* indptr, const int32_t* indices, const float* values,

@@ -37,7 +37,7 @@ def build_parser():
     ap.add_argument('--train_row', type=int, default=8000)
     ap.add_argument('--validate_row', type=int, default=2000)
     _bool_flag(ap, 'restore_previous_data', False, 'restore previous data corresponding to model name')
-    ap.add_argument('--min_df', type=float, default=0)
+    ap.add_argument('--min_df', type=float, default=0.0)
     ap.add_argument('--max_df', type=float, default=0.99)
     ap.add_argument('--max_features', type=int, default=10000)
     ap.add_argument('--model_name', default='')
@@ -56,12 +56,13 @@ def build_parser():
     ap.add_argument('--momentum', type=float, default=0.5)
     ap.add_argument('--num_epochs', type=int, default=50)
     ap.add_argument('--batch_size', type=float, default=0.1)
-    ap.add_argument('--alpha', type=float, default=1)
+    ap.add_argument('--alpha', type=float, default=1.0)
     ap.add_argument('--triplet_strategy', default='batch_all')
     # additive
     ap.add_argument('--data_path', default='datasets/uci_news.snappy.parquet')
     ap.add_argument('--synthetic', type=int, default=0, help='train on N synthetic articles instead of reading --data_path')
-    ap.add_argument('--rng_mode', default='numpy', choices=['numpy', 'device'])
+    ap.add_argument('--rng_mode', default='device', choices=['numpy', 'device'],
+                    help="'device': Philox masking + device permutation (default); 'numpy': the reference's host NumPy RNG stream")
     return ap
 
 
@@ -75,18 +76,21 @@ def apply_env_overrides(flags):
             dotenv.load_dotenv(dot_env_path)
         except ImportError:
             pass
-    for k, v in vars(flags).items():
-        if k in os.environ:
-            raw = os.environ[k]
-            if isinstance(v, bool):
-                setattr(flags, k, True)
-            elif isinstance(v, int):
-                setattr(flags, k, int(raw))
-            elif isinstance(v, float):
-                setattr(flags, k, float(raw))
-            else:
-                setattr(flags, k, raw)
+    for k, cast in _ENV_OVERRIDES.items():   # the reference's fixed list (main_autoencoder.py:75-92), with the right keys for corr_*
+        if k in os.environ and hasattr(flags, k):
+            setattr(flags, k, cast(os.environ[k]))
     return flags
+
+
+def _env_bool(raw):
+    """The reference sets a boolean flag to True when the variable merely exists; here '0' / 'false' / 'no' / '' mean False."""
+    return str(raw).strip().lower() not in ('', '0', 'false', 'no', 'off')
+
+
+_ENV_OVERRIDES = {'model_name': str, 'restore_previous_model': _env_bool, 'seed': int, 'compress_factor': int, 'corr_type': str,
+                  'corr_frac': float, 'xavier_init': int, 'enc_act_func': str, 'dec_act_func': str, 'main_dir': str, 'loss_func': str,
+                  'opt': str, 'learning_rate': float, 'momentum': float, 'num_epochs': int, 'batch_size': float, 'alpha': float,
+                  'triplet_strategy': str}
 
 
 def check_flags(F):
@@ -128,7 +132,12 @@ def prepare_uci(F, model=None):
         df.index.name = None
     df = df.sort_index(ascending=False)
     df['label_story'] = pd.factorize(df.story)[0]
-    df['label_category_publish_name'] = pd.factorize(df.category_publish_name.apply(lambda s: s.lstrip('即時')))[0]
+    cat = df.category_publish_name.apply(lambda s: s.lstrip('即時') if isinstance(s, str) else s)
+    df['label_category_publish_name'] = pd.factorize(cat)[0]
+    if F.triplet_strategy != 'none':
+        # rows without the selected label cannot be mined (reference main_autoencoder.py:181-201 keeps label_<label>_valid == 1):
+        # pd.factorize gives them -1, which would otherwise act as one large shared class
+        df = df.loc[df['label_' + F.label] >= 0]
     n_tr, n_va = F.train_row, F.validate_row
     df = df.iloc[0:n_tr + n_va].sample(frac=1)
     df = df.sort_values('article_id') if 'article_id' in df.columns else df.sort_index()
@@ -262,7 +271,7 @@ def main(argv=None):
     # inputs are decayed by (1 - corr_frac) at inference (reference main_autoencoder.py:289-290)
     enc = model.transform(utils.decay_noise(trX, F.corr_frac), name='article_encoded', save=F.encode_full)
     enc_v = model.transform(utils.decay_noise(vlX, F.corr_frac), name='article_encoded_validate', save=F.encode_full)
-    print('encoded: train %s validate %s (train_time of the last epoch: %.3f s)' % (enc.shape, enc_v.shape, model.train_time))
+    print('encoded: train %s validate %s (train_time of the last epoch: %.3f s)' % (enc.shape, enc_v.shape, model.train_time or 0.0))
     if F.save_tsv:
         save_tsv(model, data, enc, enc_v)
     model.evaluation = evaluate(F, model, trX, vlX, trL, vlL, enc, enc_v)

@@ -173,7 +173,7 @@ def main(argv=None):
     print('fit done')
     enc = model.transform(utils.decay_noise(trX['org'], F.corr_frac), name='article_encoded', save=F.encode_full)
     enc_v = model.transform(utils.decay_noise(vlX['org'], F.corr_frac), name='article_encoded_validate', save=F.encode_full)
-    print('encoded: train %s validate %s (train_time of the last epoch: %.3f s)' % (enc.shape, enc_v.shape, model.train_time))
+    print('encoded: train %s validate %s (train_time of the last epoch: %.3f s)' % (enc.shape, enc_v.shape, model.train_time or 0.0))
     if F.save_tsv:
         flat = None if data is None else {'tfidf': (data['tfidf']['train']['org'], data['tfidf']['validate']['org']),
                                           'binary': (data['binary']['train']['org'], data['binary']['validate']['org']),

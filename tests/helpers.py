@@ -6,9 +6,19 @@ REL_TOL = 1e-4  # north_star: embeddings and per-step losses within 1e-4 relativ
 
 
 def rel_err(a, b):
+    """NORM-wise relative error: max|a - b| / max|b| (the tensor's largest entry sets the scale)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
+
+
+def elem_err(a, b, floor=1e-2):
+    """Element-wise relative error: max_i |a_i - b_i| / max(|b_i|, floor * max|b|) -- every entry is compared with its OWN magnitude;
+    entries below `floor` x the tensor's scale (results of cancellation) are compared with that floor instead."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), floor * (np.max(np.abs(b)) + 1e-30))
+    return float(np.max(np.abs(a - b) / den))
 
 
 def random_csr(n, F, nnz_per_row, kind='binary', seed=0):

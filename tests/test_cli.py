@@ -32,9 +32,15 @@ def test_asserts_and_env_override(monkeypatch):
         cli.check_flags(cli.build_parser().parse_args(['--triplet_strategy', 'semi_hard']))
     monkeypatch.setenv('corr_type', 'decay')
     monkeypatch.setenv('corr_frac', '0.5')
+    monkeypatch.setenv('alpha', '0.5')                    # float flags stay floats (the reference casts with float(), :90)
+    monkeypatch.setenv('restore_previous_model', '0')     # an explicit false value is False, not "the variable exists"
+    monkeypatch.setenv('label', 'story')                  # not in the reference's override list (:75-92): ignored
     monkeypatch.setenv('verbose', '1')
     F = cli.apply_env_overrides(cli.build_parser().parse_args([]))
-    assert F.corr_type == 'decay' and F.corr_frac == 0.5 and F.verbose is True  # the reference reads compress_factor here (:79-80)
+    assert F.corr_type == 'decay' and F.corr_frac == 0.5  # the reference reads compress_factor here (:79-80)
+    assert F.alpha == 0.5 and F.restore_previous_model is False and F.label == 'category_publish_name' and F.verbose is False
+    monkeypatch.setenv('restore_previous_model', 'True')
+    assert cli.apply_env_overrides(cli.build_parser().parse_args([])).restore_previous_model is True
 
 
 @pytest.mark.gpu
@@ -50,3 +56,18 @@ def test_cli_end_to_end_on_synthetic():
         assert 0.0 <= ev[key]['auroc'] <= 1.0 and os.path.exists(model.plot_dir + key + '.json')
     idx, score = ev['nearest']
     assert idx.shape == (960,) and (idx != range(960)).all() and (score <= 1.0 + 1e-5).all()
+
+
+@pytest.mark.gpu
+def test_cli_zero_epochs_restores_and_encodes():
+    """--num_epochs 0 "will not train the model" (reference main_autoencoder.py:71): with --restore_previous_model it is the
+    restore-then-encode path; train_time stays None and the run must still save the embeddings."""
+    import numpy as np
+    common = ['--model_name', 'syn0', '--synthetic', '600', '--max_features', '1500', '--batch_size', '100', '--seed', '3',
+              '--triplet_strategy', 'none']
+    m1 = cli.main(common + ['--num_epochs', '1', '--encode_full'])
+    e1 = np.load(m1.data_dir + 'article_encoded.npy')
+    m2 = cli.main(common + ['--num_epochs', '0', '--restore_previous_model', '--encode_full'])
+    assert m2.train_time is None
+    e2 = np.load(m2.data_dir + 'article_encoded.npy')
+    assert np.array_equal(e1, e2)

@@ -9,6 +9,16 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
+@pytest.fixture(autouse=True, params=['auto', 'pair'])
+def _tile_engine(request):
+    """Every test runs twice: with the size-based choice between one-CTA tiles and CTA pairs (cta_group::2), and with the pairs
+    forced (small, ragged and single-m-tile shapes through the 2-SM kernel)."""
+    from dae_rnn_news_recommendation_b200 import _cabi
+    _cabi.call('dae_gemm_config', 1 if request.param == 'pair' else -1)
+    yield
+    _cabi.call('dae_gemm_config', -1)
+
+
 def _split(x, ld, ones_col=-1):
     from dae_rnn_news_recommendation_b200 import _cabi
     rows, cols = x.shape

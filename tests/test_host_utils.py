@@ -109,3 +109,14 @@ def test_batch_size_resolution_and_xavier():
     b = np.sqrt(6.0 / 120)
     assert W.dtype == np.float32 and W.shape == (100, 20) and np.abs(W).max() <= b
     assert O.xavier_bounds(100, 20) == (-b, b)
+
+
+def test_transform_shards_tile_the_rows():
+    """DenoisingAutoencoder.shard_rows: contiguous, disjoint, covering, balanced to within one row."""
+    from dae_rnn_news_recommendation_b200.autoencoder import DenoisingAutoencoder
+    for n in (0, 1, 7, 8000, 100003):
+        for world in (1, 2, 3, 8):
+            r = [DenoisingAutoencoder.shard_rows(n, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
