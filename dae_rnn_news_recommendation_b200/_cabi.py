@@ -35,16 +35,17 @@ _SIGNATURES = {
     'dae_batch_prepare_explicit': (C.c_int, [p, i64, p, i32, i64, p, p, p]),
     'dae_step_advance': (C.c_int, [p, i64, p]),
     'dae_encode_csr_fwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p, i64, p]),
-    'dae_encode_csr_fwd_hot': (C.c_int, [p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, i32, p]),
+    'dae_encode_csr_fwd_hot': (C.c_int, [p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, i32, i32, p]),
     'dae_col_scan': (C.c_int, [p, i32, p, p, p]),
-    'dae_encode_csr_bwd_gather': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p, p, p, p, p, p, p]),
-    'dae_encode_csr_bwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, i64, p, p, p]),
+    'dae_encode_csr_bwd_gather': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, p, i64, p, p, i32, p, p, p, p, p, p, p]),
+    'dae_encode_csr_bwd': (C.c_int, [p, p, p, p, i32, i32, i32, f32, p, p, i32, p, p, i64, p, p, i32, p]),
     'dae_sgemm': (C.c_int, [i32, i32, i32, f32, p, i64, i64, p, i64, i64, f32, p, i64, p]),
     'dae_split_bf16': (C.c_int, [p, i32, i32, i64, p, p, i64, i32, f32, p]),
     'dae_sym_split_bf16': (C.c_int, [p, i32, i64, f32, p, p, i64, p]),
     'dae_gemm_bf16x3': (C.c_int, [i32, i32, i32, f32, p, p, i64, i32, p, p, i64, i32, p, i64, i32, i32, p, i32, i32, p]),
-    'dae_gemm_config': (C.c_int, [i32]),
-    'dae_decode_fused_bf16x3': (C.c_int, [i32, i32, i32, p, p, i64, p, p, i64, p, p, p, p, p, i32, i32, p, p, p, p, i64, p, p, p]),
+    'dae_gemm_config': (C.c_int, [i32, i32]),
+    'dae_decode_prepare': (C.c_int, [i32, i32, p, p, p, p, p, p]),
+    'dae_decode_fused_bf16x3': (C.c_int, [i32, i32, i32, p, p, i64, p, p, i64, p, p, p, p, p, i32, i32, p, p, p, p, i64, p, p, i32, p]),
     'dae_reduce_parts': (C.c_int, [p, i32, i32, p, p]),
     'dae_decode_loss_bwd': (C.c_int, [p, p, p, p, i32, i32, p, i32, i32, p, p, p, i64, p, p]),
     'dae_colsum': (C.c_int, [p, i32, i32, i64, p, p]),
@@ -84,8 +85,8 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if os.environ.get('DAE_GEMM_PAIR'):   # development switch of the tile engine (see dae_gemm_config); unset = by size
-            l.dae_gemm_config(int(os.environ['DAE_GEMM_PAIR']))
+        if os.environ.get('DAE_GEMM_PAIR') or os.environ.get('DAE_GEMM_LEAN'):   # development switches of the tile engine (dae_gemm_config)
+            l.dae_gemm_config(int(os.environ.get('DAE_GEMM_PAIR', -1)), int(os.environ.get('DAE_GEMM_LEAN', 1)))
         _lib = l
     return _lib
 

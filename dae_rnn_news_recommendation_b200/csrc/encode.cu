@@ -145,12 +145,11 @@ __global__ void __launch_bounds__(kEncThreads * G) encode_fwd_kernel(
 // mbarrier) and then serves entries of those columns from shared memory; only the cold tail still gathers from L2.
 // hot_slot[col] = slot of the column in the staged set, or -1.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kHotGroups = 4;
 
 __device__ __forceinline__ uint32_t enc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int ACT, int NC>
-__global__ void __launch_bounds__(kEncThreads * kHotGroups, 1) encode_fwd_hot_kernel(
+template <int ACT, int NC, int kHotGroups>
+__global__ void __launch_bounds__(kEncThreads * kHotGroups) encode_fwd_hot_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values, int n_rows, int H,
     float in_scale, const float* __restrict__ W, const float* __restrict__ bh, float* __restrict__ E, int64_t ldE,
     const int32_t* __restrict__ hot_cols, const int32_t* __restrict__ hot_slot, int K) {
@@ -217,14 +216,13 @@ __global__ void __launch_bounds__(kEncThreads * kHotGroups, 1) encode_fwd_hot_ke
       for (int q = 0; q < cnt; ++q) {
         const float vq = s_val[grp][q];
         const int sq = s_slot[grp][q];                 // uniform over the group: no divergence
-        const float* wg = W + (int64_t)s_col[grp][q] * H;
-        const float* ws = s_w + (int64_t)(sq < 0 ? 0 : sq) * H;
+        // ONE generic-address load serves both cases (shared-memory window or global): no branch in the loop body, so the
+        // unrolled iterations keep 8 independent loads in flight per thread exactly like the row kernel
+        const float* src = (sq >= 0) ? (s_w + (int64_t)sq * H) : (W + (int64_t)s_col[grp][q] * H);
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           if (hcol[c] < H) {
-            float4 w;
-            if (sq >= 0) w = *reinterpret_cast<const float4*>(ws + hcol[c]);
-            else w = __ldg(reinterpret_cast<const float4*>(wg + hcol[c]));
+            const float4 w = *reinterpret_cast<const float4*>(src + hcol[c]);
             acc[c][0] = fmaf(vq, w.x, acc[c][0]); acc[c][1] = fmaf(vq, w.y, acc[c][1]);
             acc[c][2] = fmaf(vq, w.z, acc[c][2]); acc[c][3] = fmaf(vq, w.w, acc[c][3]);
           }
@@ -251,7 +249,7 @@ template <int ACT, int VW, int NC>
 __global__ void __launch_bounds__(kEncThreads) encode_bwd_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
     const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ E, const float* __restrict__ bh,
-    float* __restrict__ dE, int64_t ldE, float* __restrict__ dW, float* __restrict__ dbh) {
+    float* __restrict__ dE, const float* __restrict__ dE_add, int64_t ldE, float* __restrict__ dW, float* __restrict__ dbh) {
   __shared__ int s_col[kEncThreads];
   __shared__ float s_val[kEncThreads];
   __shared__ int s_wcnt[kEncThreads / 32];
@@ -273,7 +271,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_bwd_kernel(
         const float b = __ldg(bh + h);
         const float fb = act_fwd<ACT>(b);
         const float fa = E[(int64_t)r * ldE + h] + fb;
-        const float de = dE[(int64_t)r * ldE + h];
+        const float de = dE[(int64_t)r * ldE + h] + (dE_add ? dE_add[(int64_t)r * ldE + h] : 0.0f);
         const float da = de * act_grad_from_y<ACT>(fa);
         dA[c][e] = da;
         dE[(int64_t)r * ldE + h] = da;
@@ -348,34 +346,63 @@ __global__ void __launch_bounds__(1024) col_scan_kernel(const int32_t* __restric
   if (tid == 0) col_start[F] = s_carry;
 }
 
-// per batch row: dA = dE * f'(A), dbh, and the row's kept entries appended to their column buckets
+// per batch row: dA = dE * f'(A), dbh, and the row's kept entries appended to their column buckets.  A CTA takes kRowsPerCta rows
+// and keeps its dbh partial sums in registers: one atomic per hidden unit per CTA instead of one per (row, hidden unit) -- the H
+// addresses of dbh are otherwise hit by every row of the batch.
+constexpr int kRowsPerCta = 4;
+
 template <int ACT>
 __global__ void __launch_bounds__(kEncThreads) encode_bwd_rows_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-    const int32_t* __restrict__ rows, int H, float in_scale, const float* __restrict__ E, const float* __restrict__ bh,
-    float* __restrict__ dE, int64_t ldE, float* __restrict__ dbh, int32_t* __restrict__ col_cursor, int32_t* __restrict__ ent_col,
+    const int32_t* __restrict__ rows, int n_rows, int H, float in_scale, const float* __restrict__ E, const float* __restrict__ bh,
+    float* __restrict__ dE, const float* __restrict__ dE_add, int64_t ldE, float* __restrict__ dbh, int32_t* __restrict__ col_cursor, int32_t* __restrict__ ent_col,
     int32_t* __restrict__ ent_row, float* __restrict__ ent_val) {
+  constexpr int kMaxPer = 8;   // H <= 8 * 128 on this path
   const int tid = threadIdx.x;
-  const int r = blockIdx.x;
-  const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
-  const int64_t p0 = indptr[row], p1 = indptr[row + 1];
-  for (int h = tid; h < H; h += kEncThreads) {
-    const float b = __ldg(bh + h);
-    const float fb = act_fwd<ACT>(b);
-    const float fa = E[(int64_t)r * ldE + h] + fb;
-    const float de = dE[(int64_t)r * ldE + h];
-    const float da = de * act_grad_from_y<ACT>(fa);
-    dE[(int64_t)r * ldE + h] = da;
-    atomicAdd(dbh + h, da - act_grad_from_y<ACT>(fb) * de);
+  const int r0 = blockIdx.x * kRowsPerCta;
+  float fb[kMaxPer], gfb[kMaxPer], part[kMaxPer];
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int h = tid + k * kEncThreads;
+    const float b = (h < H) ? __ldg(bh + h) : 0.0f;
+    fb[k] = act_fwd<ACT>(b);
+    gfb[k] = act_grad_from_y<ACT>(fb[k]);
+    part[k] = 0.0f;
   }
-  for (int64_t p = p0 + tid; p < p1; p += kEncThreads) {
-    const float v = __ldg(values + p) * in_scale;
-    if (v != 0.0f) {
-      const int col = __ldg(indices + p);
-      const int slot = atomicAdd(col_cursor + col, 1);
-      ent_col[slot] = col;
-      ent_row[slot] = r;
-      ent_val[slot] = v;
+  for (int rr = 0; rr < kRowsPerCta; ++rr) {
+    const int r = r0 + rr;
+    if (r >= n_rows) break;
+#pragma unroll
+    for (int k = 0; k < kMaxPer; ++k) {
+      const int h = tid + k * kEncThreads;
+      if (h < H) {
+        const float fa = E[(int64_t)r * ldE + h] + fb[k];
+        const float de = dE[(int64_t)r * ldE + h] + (dE_add ? dE_add[(int64_t)r * ldE + h] : 0.0f);
+        const float da = de * act_grad_from_y<ACT>(fa);
+        dE[(int64_t)r * ldE + h] = da;
+        part[k] += da - gfb[k] * de;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxPer; ++k) {
+    const int h = tid + k * kEncThreads;
+    if (h < H) atomicAdd(dbh + h, part[k]);
+  }
+  for (int rr = 0; rr < kRowsPerCta; ++rr) {
+    const int r = r0 + rr;
+    if (r >= n_rows) break;
+    const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
+    const int64_t p0 = indptr[row], p1 = indptr[row + 1];
+    for (int64_t p = p0 + tid; p < p1; p += kEncThreads) {
+      const float v = __ldg(values + p) * in_scale;
+      if (v != 0.0f) {
+        const int col = __ldg(indices + p);
+        const int slot = atomicAdd(col_cursor + col, 1);
+        ent_col[slot] = col;
+        ent_row[slot] = r;
+        ent_val[slot] = v;
+      }
     }
   }
 }
@@ -384,7 +411,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_bwd_rows_kernel(
 // Zipfian: a few columns hold hundreds of entries): each CTA takes chunks of kChunk consecutive entries, accumulates
 // v * dA[r,:] in registers while the column stays the same and flushes one vector red.global.add per (chunk, column) run --
 // about (#touched columns + #chunks) vector atomics per step instead of one per entry.
-constexpr int kChunk = 64;
+constexpr int kChunk = 32;
 
 template <int VW, int NC>
 __global__ void __launch_bounds__(kEncThreads) encode_bwd_gather_kernel(const int32_t* __restrict__ col_start, int F,
@@ -493,13 +520,13 @@ static int launch_fwd_nc(int nc, int groups, dim3 grid, cudaStream_t st, const i
 
 template <int ACT, int VW>
 static int launch_bwd_nc(int nc, dim3 grid, cudaStream_t st, const int64_t* indptr, const int32_t* indices, const float* values,
-                         const int32_t* rows, int H, float in_scale, const float* E, const float* bh, float* dE, int64_t ldE,
-                         float* dW, float* dbh) {
+                         const int32_t* rows, int H, float in_scale, const float* E, const float* bh, float* dE, const float* dE_add,
+                         int64_t ldE, float* dW, float* dbh) {
   switch (nc) {
-    case 1: encode_bwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
-    case 2: encode_bwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
-    case 4: encode_bwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
-    default: encode_bwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh); break;
+    case 1: encode_bwd_kernel<ACT, VW, 1><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh); break;
+    case 2: encode_bwd_kernel<ACT, VW, 2><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh); break;
+    case 4: encode_bwd_kernel<ACT, VW, 4><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh); break;
+    default: encode_bwd_kernel<ACT, VW, 8><<<grid, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh); break;
   }
   return 0;
 }
@@ -550,21 +577,22 @@ extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices,
 
 extern "C" int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
                                   int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* E, const float* bh,
-                                  int32_t enc_act, float* dE, int64_t ldE, float* dW, float* dbh, void* stream) {
+                                  int32_t enc_act, float* dE, const float* dE_add, int64_t ldE, float* dW, float* dbh, int32_t dbh_zeroed,
+                                  void* stream) {
   using namespace dae;
   DAE_REQUIRE(indptr && indices && values && E && bh && dE && dW && dbh, "dae_encode_csr_bwd: null pointer");
   DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  DAE_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * H, st));
+  if (!dbh_zeroed) DAE_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * H, st));
   if (n_rows == 0) return DAE_OK;
   const int vw = pick_vw(H, H, dW);
   const int nc = pick_nc(H, vw);
   if (nc < 0) { set_error("dae_encode_csr_bwd: H=%d too large", H); return DAE_ERR_UNSUPPORTED; }
   dim3 grid(n_rows);
   DAE_DISPATCH_ACT(enc_act, ACT, {
-    if (vw == 4) launch_bwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
-    else if (vw == 2) launch_bwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
-    else launch_bwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dW, dbh);
+    if (vw == 4) launch_bwd_nc<ACT, 4>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh);
+    else if (vw == 2) launch_bwd_nc<ACT, 2>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh);
+    else launch_bwd_nc<ACT, 1>(nc, grid, st, indptr, indices, values, rows, H, in_scale, E, bh, dE, dE_add, ldE, dW, dbh);
   });
   DAE_CHECK_LAUNCH("dae_encode_csr_bwd");
   return DAE_OK;
@@ -572,15 +600,15 @@ extern "C" int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices,
 
 extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* rows,
                                          int32_t n_rows, int32_t F, int32_t H, float in_scale, const float* E, const float* bh,
-                                         int32_t enc_act, float* dE, int64_t ldE, float* dW, float* dbh, const int32_t* col_count,
-                                         int32_t* col_start, int32_t* col_cursor, int32_t* ent_col, int32_t* ent_row,
-                                         float* ent_val, void* stream) {
+                                         int32_t enc_act, float* dE, const float* dE_add, int64_t ldE, float* dW, float* dbh,
+                                         int32_t dbh_zeroed, const int32_t* col_count, int32_t* col_start, int32_t* col_cursor,
+                                         int32_t* ent_col, int32_t* ent_row, float* ent_val, void* stream) {
   using namespace dae;
   DAE_REQUIRE(indptr && indices && values && E && bh && dE && dW && dbh && col_start && col_cursor && ent_col && ent_row && ent_val,
               "dae_encode_csr_bwd_gather: null pointer");
   DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H, "dae_encode_csr_bwd_gather: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  DAE_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * H, st));
+  if (!dbh_zeroed) DAE_CUDA(cudaMemsetAsync(dbh, 0, sizeof(float) * H, st));
   if (n_rows == 0) return DAE_OK;
   int vw = pick_vw(H, ldE, dE);
   if (pick_vw(H, H, dW) < vw) vw = pick_vw(H, H, dW);
@@ -588,10 +616,10 @@ extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* i
   if (nc < 0 || nc > 2) { set_error("dae_encode_csr_bwd_gather: H=%d not supported (use dae_encode_csr_bwd)", H); return DAE_ERR_UNSUPPORTED; }
   if (col_count) col_scan_kernel<<<1, 1024, 0, st>>>(col_count, F, col_start, col_cursor);  // NULL: dae_col_scan already ran
   DAE_DISPATCH_ACT(enc_act, ACT, {
-    encode_bwd_rows_kernel<ACT><<<n_rows, kEncThreads, 0, st>>>(indptr, indices, values, rows, H, in_scale, E, bh, dE, ldE, dbh, col_cursor,
+    encode_bwd_rows_kernel<ACT><<<(n_rows + kRowsPerCta - 1) / kRowsPerCta, kEncThreads, 0, st>>>(indptr, indices, values, rows, n_rows, H, in_scale, E, bh, dE, dE_add, ldE, dbh, col_cursor,
                                                                ent_col, ent_row, ent_val);
   });
-#define DAE_GATHER(VW, NC) encode_bwd_gather_kernel<VW, NC><<<148 * 8, kEncThreads, 0, st>>>(col_start, F, ent_col, ent_row, ent_val, H, dE, ldE, dW)
+#define DAE_GATHER(VW, NC) encode_bwd_gather_kernel<VW, NC><<<148 * 16, kEncThreads, 0, st>>>(col_start, F, ent_col, ent_row, ent_val, H, dE, ldE, dW)
 #define DAE_GATHER_NC(VW) \
   do { if (nc == 1) DAE_GATHER(VW, 1); else DAE_GATHER(VW, 2); } while (0)
   if (vw == 4) DAE_GATHER_NC(4); else if (vw == 2) DAE_GATHER_NC(2); else DAE_GATHER_NC(1);
@@ -611,7 +639,7 @@ extern "C" int dae_col_scan(const int32_t* col_count, int32_t F, int32_t* col_st
 
 extern "C" int dae_encode_csr_fwd_hot(const int64_t* indptr, const int32_t* indices, const float* values, int32_t n_rows, int32_t F,
                                       int32_t H, float in_scale, const float* W, const float* bh, int32_t enc_act, float* E, int64_t ldE,
-                                      const int32_t* hot_cols, const int32_t* hot_slot, int32_t K, void* stream) {
+                                      const int32_t* hot_cols, const int32_t* hot_slot, int32_t K, int32_t groups, void* stream) {
   using namespace dae;
   DAE_REQUIRE(indptr && indices && values && W && bh && E && hot_cols && hot_slot, "dae_encode_csr_fwd_hot: null pointer");
   DAE_REQUIRE(n_rows >= 0 && F > 0 && H > 0 && ldE >= H && K >= 1, "dae_encode_csr_fwd_hot: bad shape");
@@ -625,14 +653,23 @@ extern "C" int dae_encode_csr_fwd_hot(const int64_t* indptr, const int32_t* indi
   DAE_CUDA(cudaGetDevice(&dev));
   DAE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int nc = (H + 4 * kEncThreads - 1) / (4 * kEncThreads);
-  const int grid = (n_rows + kHotGroups - 1) / kHotGroups < sms ? (n_rows + kHotGroups - 1) / kHotGroups : sms;
-#define DAE_HOT(ACT, NC)                                                                                                          \
+  const int G = (groups >= 8) ? 8 : 4;
+  // CTAs per SM follow from the staged set: one for K * H * 4 > 100 KB, two up to 100 KB, three up to 64 KB ...
+  int per_sm = (int)((220 * 1024) / (smem + 8 * 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * G * kEncThreads > 2048) per_sm = 2048 / (G * kEncThreads);
+  const int want = (n_rows + G - 1) / G;
+  const int grid = want < sms * per_sm ? want : sms * per_sm;
+#define DAE_HOT(ACT, NC, GG)                                                                                                       \
   do {                                                                                                                            \
-    auto kern = encode_fwd_hot_kernel<ACT, NC>;                                                                                   \
+    auto kern = encode_fwd_hot_kernel<ACT, NC, GG>;                                                                               \
     DAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                                \
-    kern<<<grid, kEncThreads * kHotGroups, smem, st>>>(indptr, indices, values, n_rows, H, in_scale, W, bh, E, ldE, hot_cols, hot_slot, K); \
+    kern<<<grid, kEncThreads * GG, smem, st>>>(indptr, indices, values, n_rows, H, in_scale, W, bh, E, ldE, hot_cols, hot_slot, K); \
   } while (0)
-  DAE_DISPATCH_ACT(enc_act, ACT, { if (nc <= 1) DAE_HOT(ACT, 1); else DAE_HOT(ACT, 2); });
+  DAE_DISPATCH_ACT(enc_act, ACT, {
+    if (G == 8) { if (nc <= 1) DAE_HOT(ACT, 1, 8); else DAE_HOT(ACT, 2, 8); }
+    else { if (nc <= 1) DAE_HOT(ACT, 1, 4); else DAE_HOT(ACT, 2, 4); }
+  });
 #undef DAE_HOT
   DAE_CHECK_LAUNCH("dae_encode_csr_fwd_hot");
   return DAE_OK;

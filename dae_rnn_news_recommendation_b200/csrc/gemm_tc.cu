@@ -818,6 +818,7 @@ static int sm_count() {
 }
 
 static int g_pair_mode = -1;   // -1: by size (dae_gemm_config); 0: never; 1: whenever the shape allows
+static int g_lean = 1;         // 1: leave ~70 KB of each SM's shared memory to concurrently running kernels (2-stage pipelines)
 
 template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS, int PAIR>
 static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStream_t st) {
@@ -874,6 +875,9 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
   return DAE_OK;
 }
 
+// column-tile width of the fused decode kernel under the current configuration (dae_decode_prepare lays tile_ptr out for it)
+static int decode_tile_width() { return (g_pair_mode == 1 || !g_lean) ? 256 : 128; }
+
 // CTA pairs pay off once the GEMM is large enough to be bound by L2 -> SM operand traffic (>= ~2 GFLOP here: decode, dW, dE)
 static bool use_pair(int M, int N, int K) {
   if (g_pair_mode == 0) return false;
@@ -905,7 +909,11 @@ extern "C" int dae_sym_split_bf16(const float* G, int32_t B, int64_t ldg, float 
 }
 
 // test hook: -1 = CTA pairs (cta_group::2) for the large GEMMs only (default), 0 = never, 1 = always
-extern "C" int dae_gemm_config(int32_t pair_mode) { dae::g_pair_mode = pair_mode < 0 ? -1 : (pair_mode ? 1 : 0); return DAE_OK; }
+extern "C" int dae_gemm_config(int32_t pair_mode, int32_t lean) {
+  dae::g_pair_mode = pair_mode < 0 ? -1 : (pair_mode ? 1 : 0);
+  dae::g_lean = lean ? 1 : 0;
+  return DAE_OK;
+}
 
 extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_hi, const void* a_lo, int64_t lda,
                                int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb, int32_t b_mn_major, float* C,
@@ -946,7 +954,7 @@ extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, con
   int rc;
   const int tiles256 = tm * tn256 * k_splits, tiles128 = tm * tn128 * k_splits;
   const float cost256 = 2.0f * (float)((tiles256 + sms - 1) / sms), cost128 = 1.1f * (float)((tiles128 + sms - 1) / sms);
-  if (use_pair(M, N, K)) rc = launch_gemm<256, 3, EPI_STORE, 0, 0, 1>(A, B, p, st);
+  if (use_pair(M, N, K)) rc = g_lean ? launch_gemm<256, 2, EPI_STORE, 0, 0, 1>(A, B, p, st) : launch_gemm<256, 3, EPI_STORE, 0, 0, 1>(A, B, p, st);
   else if (!stream_k && cost128 < cost256) rc = launch_gemm<128, 3, EPI_STORE, 0, 0, 0>(A, B, p, st);
   else rc = launch_gemm<256, 2, EPI_STORE, 0, 0, 0>(A, B, p, st);
   if (rc) return rc;
@@ -954,11 +962,24 @@ extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, con
   return DAE_OK;
 }
 
+extern "C" int dae_decode_prepare(int32_t Brows, int32_t F, const int64_t* indptr, const int32_t* indices, const int32_t* rows,
+                                  float* row_loss_part, int32_t* tile_ptr, void* stream) {
+  DAE_REQUIRE(Brows > 0 && F > 0 && indptr && indices && row_loss_part && tile_ptr, "dae_decode_prepare: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DAE_CUDA(cudaMemsetAsync(row_loss_part, 0, sizeof(float) * Brows, st));
+  const int width = decode_tile_width();                              // column tile of the fused decode kernel that will consume this
+  const int n_half = (kEwDecode / 4) * ((F + width - 1) / width);
+  dim3 grid((n_half + 1 + 127) / 128, Brows);
+  decode_tile_ptr_kernel<<<grid, 128, 0, st>>>(indptr, indices, rows, Brows, n_half, width / (kEwDecode / 4), tile_ptr);
+  DAE_CHECK_LAUNCH("dae_decode_prepare");
+  return DAE_OK;
+}
+
 extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo, int64_t lde,
                                        const void* w_hi, const void* w_lo, int64_t ldw, const int64_t* indptr, const int32_t* indices,
                                        const float* values, const int32_t* rows, const float* bv, int32_t dec_act, int32_t loss_func,
                                        const float* weight, const double* stats, void* dz_hi, void* dz_lo, int64_t ld_dz,
-                                       float* row_loss_part, int32_t* tile_ptr, void* stream) {
+                                       float* row_loss_part, int32_t* tile_ptr, int32_t prepared, void* stream) {
   DAE_REQUIRE(e_hi && e_lo && w_hi && w_lo && indptr && indices && values && bv && stats && dz_hi && dz_lo && row_loss_part && tile_ptr,
               "dae_decode_fused_bf16x3: null pointer");
   DAE_REQUIRE(loss_func == DAE_LOSS_CE || loss_func == DAE_LOSS_MSE, "dae_decode_fused_bf16x3: cosine loss uses the unfused path");
@@ -969,16 +990,19 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
   p.indptr = indptr; p.indices = indices; p.values = values; p.rows = rows; p.bv = bv; p.weight = weight; p.stats = stats;
   p.dz_hi = (__nv_bfloat16*)dz_hi; p.dz_lo = (__nv_bfloat16*)dz_lo; p.ld_dz = ld_dz; p.row_loss_part = row_loss_part;
   p.tile_ptr = tile_ptr;
-  DAE_CUDA(cudaMemsetAsync(row_loss_part, 0, sizeof(float) * Brows, st));
-  {
-    const int n_half = (kEwDecode / 4) * ((F + 255) / 256);
-    dim3 grid((n_half + 1 + 127) / 128, Brows);
-    decode_tile_ptr_kernel<<<grid, 128, 0, st>>>(indptr, indices, rows, Brows, n_half, 256 / (kEwDecode / 4), tile_ptr);
+  if (!prepared) {   // dae_decode_prepare not issued by the caller (e.g. on a parallel graph branch): do it in line
+    int rc0 = dae_decode_prepare(Brows, F, indptr, indices, rows, row_loss_part, tile_ptr, stream);
+    if (rc0) return rc0;
   }
   Operand A{e_hi, e_lo, lde, 0}, B{w_hi, w_lo, ldw, 0};
   int rc = 0;
-  const bool pair = use_pair(Brows, F, K);
-#define DAE_DEC(ACT, LOSS) rc = pair ? launch_gemm<256, 3, EPI_DECODE, ACT, LOSS, 1>(A, B, p, st) : launch_gemm<256, 2, EPI_DECODE, ACT, LOSS, 0>(A, B, p, st)
+  // measured at C2 (800 x 10000 x 500): the pair kernel's 3 rounds of 160 pair tiles on 74 SM pairs lose to 2 rounds of 280
+  // single-CTA tiles (56 vs 47 us) -- the fused epilogue, not operand traffic, bounds this kernel; pairs only when forced (tests)
+  const bool pair = (g_pair_mode == 1);
+  // lean: 128 x 128 tiles, 2 stages = 128 KB of operand ring instead of 192 KB (same speed: 39.4 vs 37.9 us standalone at C2), so that
+  // the batch_all sweep and the CUDA-core mining GEMMs can run on the same SMs while this kernel's tensor pipe works
+#define DAE_DEC(ACT, LOSS) rc = pair ? launch_gemm<256, 3, EPI_DECODE, ACT, LOSS, 1>(A, B, p, st) \
+                              : (g_lean ? launch_gemm<128, 2, EPI_DECODE, ACT, LOSS, 0>(A, B, p, st) : launch_gemm<256, 2, EPI_DECODE, ACT, LOSS, 0>(A, B, p, st))
   if (loss_func == DAE_LOSS_CE) {
     if (dec_act == DAE_ACT_SIGMOID) DAE_DEC(DAE_ACT_SIGMOID, DAE_LOSS_CE);
     else if (dec_act == DAE_ACT_TANH) DAE_DEC(DAE_ACT_TANH, DAE_LOSS_CE);

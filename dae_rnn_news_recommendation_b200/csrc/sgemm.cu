@@ -1,6 +1,9 @@
-// fp32 CUDA-core GEMM with generic strides: the validation path for the dense contractions.
-// (The production path for these contractions is the tcgen05 kernel in gemm_tc.cu; this one exists so the
-//  tensor-core kernels can be checked on the GPU at full size, and for shapes the tensor-core path rejects.)
+// fp32 CUDA-core GEMM with generic strides.  Two jobs:
+//  * the validation path for the large dense contractions (the production path is the tcgen05 kernel in gemm_tc.cu), so the
+//    tensor-core kernels can be checked on the GPU at full size;
+//  * the production path of the two SMALL contractions of the mining branch (S = E.E^T and dE2 = alpha (G + G^T) E, 0.64 GFLOP each):
+//    a persistent tcgen05 CTA owns its SM's shared memory, so a small tensor-core GEMM cannot start while a large one runs; this
+//    kernel needs 17 KB and the FFMA pipe, and runs NEXT TO the tensor-core decode chain.
 #include "common.cuh"
 
 namespace dae {
@@ -86,11 +89,11 @@ extern "C" int dae_sgemm(int32_t M, int32_t N, int32_t K, float alpha, const flo
   DAE_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "dae_sgemm: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
-  // split-K when the tile grid cannot fill the 148 SMs and K is long (dE = dZ.W has K = F)
+  // split-K when the tile grid cannot fill the 148 SMs: ~2 CTAs per SM, k chunks of at least 64
   int splits = 1;
   const int tiles = grid.x * grid.y;
-  if (tiles < 148 && K >= 2048) {
-    splits = min((148 * 2 + tiles - 1) / tiles, K / 512);
+  if (tiles < 148 && K >= 256) {
+    splits = min((148 * 2 + tiles - 1) / tiles, K / 64);
     if (splits < 1) splits = 1;
   }
   int kchunk = (K + splits - 1) / splits;

@@ -24,6 +24,35 @@ __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ft
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot for two lanes.  The sweep is bound by instruction
+// issue, so the tier-0 tile packs its 4 x 4 triplets as 2 row pairs x 4 columns and runs every multiply / add on register pairs.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// TIER 0 on row pairs: U = (u_a, u_a'), V[b] = (v_b, v_b).  Same arithmetic as triplet_tile<0> below (e = u v, t = 1 + e, one
+// log2 and one reciprocal per four t's of a ROW), lane-wise.  rs += row sums of sigma (pair), cs[b] += column sums (pair: the two
+// rows still separate), lg += sum of log2(1 + e).
+__device__ __forceinline__ void triplet_pair_tile(f2 U, const f2 (&V)[kTK], f2& rs, f2 (&cs)[kTK], float& lg) {
+  const f2 one = pk(1.0f, 1.0f);
+  f2 e[kTK], t[kTK];
+#pragma unroll
+  for (int b = 0; b < kTK; ++b) { e[b] = mul2(U, V[b]); t[b] = fma2(U, V[b], one); }
+  const f2 p01 = mul2(t[0], t[1]), p23 = mul2(t[2], t[3]), P = mul2(p01, p23);
+  float Px, Py;
+  upk(P, Px, Py);
+  lg += fast_lg2(Px) + fast_lg2(Py);
+  const f2 r = pk(fast_rcp(Px), fast_rcp(Py));
+  const f2 r01 = mul2(r, p23), r23 = mul2(r, p01);
+  const f2 s0 = mul2(e[0], mul2(r01, t[1])), s1 = mul2(e[1], mul2(r01, t[0]));
+  const f2 s2 = mul2(e[2], mul2(r23, t[3])), s3 = mul2(e[3], mul2(r23, t[2]));
+  rs = add2(rs, add2(add2(s0, s1), add2(s2, s3)));
+  cs[0] = add2(cs[0], s0); cs[1] = add2(cs[1], s1); cs[2] = add2(cs[2], s2); cs[3] = add2(cs[3], s3);
+}
+
 // One 4 x 4 register tile of triplets: sg[a][b] = sigmoid(x_ab) = e/(1+e) with e = exp(x_ab) = u_a v_b (computed as e * 1/(1+e),
 // which keeps full relative accuracy when sigmoid is tiny), lg += sum of log2(1 + e).
 //   TIER 0 (row range < 10): t = 1 + e <= 2.2e4, so products of four t's stay finite: ONE lg2 and ONE rcp per four
@@ -84,6 +113,36 @@ __device__ __forceinline__ void triplet_sweep(const float* sj, const float* uj, 
     float s_j[kTJ], u_j[kTJ], rs[kTJ];
 #pragma unroll
     for (int a = 0; a < kTJ; ++a) { s_j[a] = sj[jt + ty * kTJ + a]; u_j[a] = uj[jt + ty * kTJ + a]; rs[a] = 0.0f; }
+    if (TIER == 0) {   // packed fp32x2 path
+      const f2 U01 = pk(u_j[0], u_j[1]), U23 = pk(u_j[2], u_j[3]);
+      f2 rs01 = pk(0.0f, 0.0f), rs23 = pk(0.0f, 0.0f);
+      for (int kt = 0; kt < Pk; kt += kKTile) {
+        const int q0 = kt + tx * kTK;
+        const float4 s4 = *reinterpret_cast<const float4*>(sk + q0);
+        const float4 v4 = *reinterpret_cast<const float4*>(vk + q0);
+        const float s_k[kTK] = {s4.x, s4.y, s4.z, s4.w};
+        const f2 V[kTK] = {pk(v4.x, v4.x), pk(v4.y, v4.y), pk(v4.z, v4.z), pk(v4.w, v4.w)};
+        f2 cs[kTK] = {pk(0.0f, 0.0f), pk(0.0f, 0.0f), pk(0.0f, 0.0f), pk(0.0f, 0.0f)};
+        triplet_pair_tile(U01, V, rs01, cs, lacc);
+        triplet_pair_tile(U23, V, rs23, cs, lacc);
+#pragma unroll
+        for (int a = 0; a < kTJ; ++a) {
+#pragma unroll
+          for (int b = 0; b < kTK; ++b)   // (S_ik - S_ij) > 1e-16 (triplet_loss_utils.py:114): one compare + one predicated add
+            asm("{ .reg .pred p; setp.gt.f32 p, %1, %2; @p add.s32 %0, %0, 1; }" : "+r"(npos) : "f"(s_k[b]), "f"(s_j[a]));
+        }
+        float4* g = reinterpret_cast<float4*>(gk + ty * Pk_max + q0);
+        float4 o = *g;
+        float lo, hi;
+        upk(cs[0], lo, hi); o.x += lo + hi;
+        upk(cs[1], lo, hi); o.y += lo + hi;
+        upk(cs[2], lo, hi); o.z += lo + hi;
+        upk(cs[3], lo, hi); o.w += lo + hi;
+        *g = o;
+      }
+      upk(rs01, rs[0], rs[1]);
+      upk(rs23, rs[2], rs[3]);
+    } else
     for (int kt = 0; kt < Pk; kt += kKTile) {
       const int q0 = kt + tx * kTK;
       const float4 s4 = *reinterpret_cast<const float4*>(sk + q0);

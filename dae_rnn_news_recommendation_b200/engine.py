@@ -132,6 +132,10 @@ class TrainEngine:
         # dense contractions: 'tc' = tcgen05 bf16x3 kernels (production), 'ffma' = fp32 CUDA-core validation kernels
         self.gemm_mode = gemm or os.environ.get('DAE_GEMM', 'tc')
         assert self.gemm_mode in ('tc', 'ffma')
+        # the two SMALL contractions of the mining branch (S = E.E^T, dE2 = alpha (G + G^T) E; 0.64 GFLOP each): 'ffma' = the fp32
+        # CUDA-core kernel, which needs 17 KB of shared memory and runs NEXT TO the persistent tcgen05 CTAs of the decode chain;
+        # 'tc' = the tensor-core kernel, which has to wait for an SM's whole shared memory
+        self.small_gemm = os.environ.get('DAE_SMALL_GEMM', 'tc') if self.gemm_mode == 'tc' else 'ffma'
         # encode backward: 'gather' = column-bucketed, atomic-free dW accumulation; 'atomic' = red.global.add per entry
         self.enc_bwd_mode = os.environ.get('DAE_ENC_BWD', 'gather')
         if self.H > (1024 if self.H % 4 == 0 else (512 if self.H % 2 == 0 else 256)):
@@ -152,9 +156,21 @@ class TrainEngine:
         # gradient exchange of the data-parallel step: 'nccl' = eager ncclAllReduce between two captured graphs, 'nccl_graph' = the
         # NCCL all-reduce captured inside the step's graph, 'multimem' = in-switch reduction by dae_allreduce_multimem (a plain
         # kernel, captured inside the step's graph; needs NVSwitch multicast)
-        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'nccl')) if self.world > 1 else 'none'
-        assert self.allreduce_mode in ('none', 'nccl', 'nccl_graph', 'multimem')
-        if self.allreduce_mode == 'multimem':
+        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'auto')) if self.world > 1 else 'none'
+        assert self.allreduce_mode in ('none', 'auto', 'nccl', 'nccl_graph', 'multimem')
+        if self.allreduce_mode == 'auto':      # in-switch exchange where the fabric offers multicast, NCCL inside the graph otherwise
+            try:
+                self._setup_multimem()
+                ok = 1
+            except Exception:   # noqa: BLE001 -- no multicast / symmetric memory on this fabric
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=self.pg)   # all ranks take the same path
+            self.allreduce_mode = 'multimem' if int(flag.item()) == 1 else 'nccl_graph'
+            if self.allreduce_mode != 'multimem' and hasattr(self, '_mm'):
+                del self._mm
+                self.grad = torch.zeros(n, **f32)
+        elif self.allreduce_mode == 'multimem':
             self._setup_multimem()
 
     # ---- kernel launch plumbing --------------------------------------------------------------------------------------
@@ -199,7 +215,10 @@ class TrainEngine:
             self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
             if fixed:   # capture the step on this layout (restores the parameters after its warm-up steps)
                 saved = (self._graph, self._graph2, getattr(self, '_graph_meta', None))
-                g = self.capture_step_graph(None, B, None, row_stride=0, staged=False)
+                if self.strategy == 3:   # explicit triplets: the feed holds the stacked [org; pos; neg] rows of the batch
+                    g = self.capture_step_graph(None, B // 3, None, row_stride=0, staged=False, explicit_n=B // 3)
+                else:
+                    g = self.capture_step_graph(None, B, None, row_stride=0, staged=False)
                 self._feed_graph = (key, g, self._graph2)
                 self._graph, self._graph2, self._graph_meta = saved
                 self._ctl_owner = None
@@ -208,12 +227,61 @@ class TrainEngine:
                 self.ctl.copy_(torch.tensor([0, 0, self.step_count + 1, 0], dtype=torch.int64))
                 self._ctl_owner = 'feed'
             self._replay(self._feed_graph[1], self._feed_graph[2])
+        elif self.strategy == 3:
+            self.step_explicit(None, 0, B // 3, B // 3, stats_log_row)
         else:
             self.step(None, 0, B, stats_log_row)
         self._stats_host.copy_(self.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         s = self._stats_host.numpy()
         return {k: float(s[i]) for k, i in STAT.items()}
+
+    def run_feeds(self, feeds):
+        """A stream of host feeds (same layout: built with one `cap_nnz`), the input pipeline of a training loop: feed i+1's
+        H2D copy runs on a copy stream while step i computes (two device staging buffers), every step's scalars leave through an
+        asynchronous D2H copy into a pinned ring, and the host synchronises once, after the last step.  Returns the list of per-step
+        stats dicts (identical to calling run_feed on each feed in turn)."""
+        feeds = list(feeds)
+        if not feeds:
+            return []
+        f0 = feeds[0]
+        assert all(f.cap_nnz is not None and (f.B, f.nnz, f.has_labels, f.F, f.nbytes) == (f0.B, f0.nnz, f0.has_labels, f0.F, f0.nbytes)
+                   for f in feeds), 'run_feeds needs feeds of one common layout (HostFeed(..., cap_nnz=...))'
+        out = [self.run_feed(f0)]            # captures the step on this layout if it has not been yet
+        n = len(feeds) - 1
+        if n == 0:
+            return out
+        if getattr(self, '_feed_stage', None) is None or self._feed_stage[0].numel() < f0.nbytes:
+            self._feed_stage = [torch.empty(self._feed_dev.numel(), dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        ring = torch.empty(n, STAT_SLOTS, dtype=torch.float64).pin_memory()
+        main, cs = torch.cuda.current_stream(), self._copy_stream
+        ev_copy = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_used = [None, None]
+        nb = f0.nbytes
+
+        def issue_copy(i):
+            k = i & 1
+            if ev_used[k] is not None:
+                cs.wait_event(ev_used[k])        # the staging buffer's previous content has been consumed
+            with torch.cuda.stream(cs):
+                self._feed_stage[k][:nb].copy_(feeds[i + 1].host, non_blocking=True)
+                ev_copy[k].record(cs)
+        issue_copy(0)
+        for i in range(n):
+            k = i & 1
+            if i + 1 < n:
+                issue_copy(i + 1)
+            main.wait_event(ev_copy[k])
+            self._feed_dev[:nb].copy_(self._feed_stage[k][:nb], non_blocking=True)      # device-to-device, into the graph's buffer
+            ev_used[k] = torch.cuda.Event()
+            ev_used[k].record(main)
+            self._replay(self._feed_graph[1], self._feed_graph[2])
+            ring[i].copy_(self.stats, non_blocking=True)
+        main.synchronize()
+        r = ring.numpy()
+        out.extend({k: float(r[i, j]) for k, j in STAT.items()} for i in range(n))
+        return out
 
     # ---- parameter views -----------------------------------------------------------------------------------------
     @property
@@ -259,6 +327,7 @@ class TrainEngine:
         i32 = dict(dtype=torch.int32, device=self.device)
         self.E = torch.empty(B, self.H, **f32)
         self.dE = torch.empty(B, self.H, **f32)
+        self.dE2 = torch.empty(B, self.H, **f32)   # triplet part of dL/dE, alpha (G + G^T) E (written on the mining branch)
         self.Z = torch.empty(B, self.F, **f32)
         self.row_loss = torch.empty(B, **f32)
         self.weight = torch.empty(B, **f32)
@@ -383,6 +452,7 @@ class TrainEngine:
         else:
             self._k('dae_batch_prepare', ptr(perm), int(offset), ptr(ctl), B, ptr(self.labels), strat, ptr(self.rows), ptr(self.labels_b),
                     ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.weight), ptr(self.stats), st)
+        self._branch_b_prologue(B, train)
         self._encode_forward(B, train)
         self._train_tail(B, strat, self.weight if strat != 0 else None, stats_log_row, train,
                          stage_next=(perm, staged) if use_stage else None)
@@ -398,6 +468,28 @@ class TrainEngine:
         s = self._stage
         self._k('dae_batch_prepare', ptr(perm), int(offset), None, B, ptr(self.labels), self.strategy, ptr(s[0]), ptr(s[1]), ptr(s[2]),
                 ptr(s[3]), ptr(s[4]), ptr(s[5]), _stream())
+
+    def _branch_b_prologue(self, B, train):
+        """Start of branch B, forked BEFORE K1: everything the later kernels need that depends on nothing but the batch's row ids --
+        zero the gradient buffer (dense dW, sparse dW and dbh accumulate into it) and dE (its stream-K GEMM accumulates), and the
+        row-id part of the fused decode (row-loss zeroing, per-tile CSR offsets).  All of it runs next to K1, off the critical path."""
+        self._branch_b = (0, None)
+        if not (self.gemm_mode == 'tc' and train and self.fork_branches):
+            return
+        main, sideB = torch.cuda.current_stream(), self._side_stream(1)
+        self._fork(main, sideB)
+        prepared = 0
+        with torch.cuda.stream(sideB):
+            self.grad.zero_()
+            self.dE.zero_()
+            if self.loss != 2:
+                c = self.csr
+                self._k('dae_decode_prepare', B, self.F, ptr(c.indptr), ptr(c.indices), ptr(self.rows), ptr(self.row_loss),
+                        ptr(self.tile_ptr), sideB.cuda_stream)
+                prepared = 1
+            ev = torch.cuda.Event()
+            ev.record(sideB)
+        self._branch_b = (prepared, ev)
 
     def _encode_forward(self, B, train):
         """K1 on the batch rows; also emits E as the bf16 hi/lo pair (plus the all-ones column kept in E_hi) the tensor-core GEMMs
@@ -416,11 +508,12 @@ class TrainEngine:
     def _train_tail(self, B, strat, weight, stats_log_row, train, stage_next=None, explicit_B=0):
         """Everything after the encode forward.  Dependencies of the step (tensor-core path):
 
-            K1 -+-> decode(+loss, dZ) -> dE = dZ.W -+-> dE += a(G+G^T)E -> encode backward (dA, dbh, sparse dW) -+-> exchange, optimizer
-                |                                   |                                                          |
-                +-> [mining: S, triplets, G+G^T] ---+        dW = dZ^T.[E|1] (dense dW, dbv) ------------------+
-                +-> zero grad                                 (branch B, starts once dE and dE_tri own the SMs)
-                     [finalize, stage next batch] (tail of the mining branch)
+            batch -+-> K1 -+-> decode(+loss, dZ) -> dE = dZ.W ----------+-> encode backward (dA, dbh, sparse dW) -+-> exchange, optimizer
+                   |       |                                            |      dA = f'(A) (dE + dE2)             |
+                   |       +-> [A: S = E.E^T, triplets, dE2 = a(G+G^T)E]+                                         |
+                   |              ... [finalize, stage next batch] (tail of branch A)                            |
+                   +-> [B: zero grad / dE, decode row-id tables] ........ dW = dZ^T.[E|1] (dense dW, dbv) --------+
+                                                                          (issued once dE owns the SMs)
 
         batch_all's mining needs only E (its data weights are closed-form) and runs as branch A next to the decode chain; the
         dense dW GEMM only meets the sparse dW of the encode backward in the (zeroed) gradient buffer, where both accumulate, so it
@@ -433,35 +526,43 @@ class TrainEngine:
         par = tc and train and self.fork_branches                   # branch B exists
         fork = par and strat == 1                                   # branch A exists
         rows = self.rows
-        sideA = self._side_stream(0) if (fork or stage_next) else None
+        sideA = self._side_stream(0) if (par or stage_next) else None
         sideB = self._side_stream(1) if par else None
+        ev_mined, used_a = None, False
         if fork:
+            used_a = True
             self._fork(main, sideA)
             with torch.cuda.stream(sideA):
                 if gather:   # the column-bucket offsets of the backward gather only need the forward kernel's counts
                     self._k('dae_col_scan', ptr(self.col_count), F, ptr(self.col_start), ptr(self.col_cursor), sideA.cuda_stream)
                     self._scan_done = True
                 self._mining(B, strat, tc)
-                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
-                        sideA.cuda_stream)
+                self._dE_triplet(B, sideA)
                 ev_mined = torch.cuda.Event()
                 ev_mined.record(sideA)
         elif strat in (1, 2):
-            self._mining(B, strat, tc)
+            self._mining(B, strat, tc)            # in line: batch_hard's data weights come out of the mining kernel
+            if tc and train and par:              # ... but its dE contribution can still run next to the decode chain
+                used_a = True
+                self._fork(main, sideA)
+                self._dE_triplet(B, sideA)
+                ev_mined = torch.cuda.Event()
+                ev_mined.record(sideA)
+            elif tc and train:
+                self._dE_triplet(B, main)
+        dec_prepared, ev_zero = 0, None
         if par:
-            self._fork(main, sideB)
-            with torch.cuda.stream(sideB):
-                self.grad.zero_()
-                ev_zero = torch.cuda.Event()
-                ev_zero.record(sideB)
+            dec_prepared, ev_zero = self._branch_b
+            main.wait_event(ev_zero)              # zeroed gradient / dE buffers, decode row-id tables (issued before K1)
         if stage_next is not None and not fork:   # (batch_hard) the staging buffers were consumed by dae_batch_commit: refill them now
+            used_a = True
             self._fork(main, sideA)
             with torch.cuda.stream(sideA):
                 self._stage_next_batch(stage_next[0], stage_next[1], B, sideA)
         if not tc:
             self._decode_and_backward(B, rows, weight, train)
         else:
-            self._decode_tc(B, rows, weight, train)
+            self._decode_tc(B, rows, weight, train, prepared=dec_prepared)
         if not train:
             if explicit_B:   # forward only: the kernel's loss statistics are what is wanted, its dE contribution lands in scratch
                 E, d, Bx = self.E, self.dE, explicit_B
@@ -479,30 +580,24 @@ class TrainEngine:
             Whl, dZhl = (self.W_hi, self.W_lo), (self.dZ_hi, self.dZ_lo)
             if not par:   # in line: the dense dW is stored first, the encode backward then adds its sparse part
                 self._dW_gemm(B, accumulate=0)
-            # k_splits = -1: stream-K (the 14 tiles of dE / 158 tiles of dW do not fill the 148 SMs in whole waves)
-            self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=-1, tag='gemm_decode_dE')
+            # k_splits = -1: stream-K (the 14 tiles of dE / 158 tiles of dW do not fill the 148 SMs in whole waves); with branch B
+            # the output was zeroed there, so the GEMM accumulates and needs no memset node of its own
+            self._tc_gemm(B, H, F, 1.0, dZhl, 0, Whl, 1, self.dE, H, k_splits=-1, accumulate=1 if par else 0, tag='gemm_decode_dE')
         if explicit_B:   # explicit (org, pos, neg) triplets: row-wise softplus(e.e- - e.e+), adds its dE (autoencoder_triplet.py:303-314)
             E, d, Bx = self.E, self.dE, explicit_B
             self._k('dae_triplet_explicit', ptr(E[0:Bx]), ptr(E[Bx:2 * Bx]), ptr(E[2 * Bx:3 * Bx]), Bx, H, H, self.alpha, ptr(d[0:Bx]),
                     ptr(d[Bx:2 * Bx]), ptr(d[2 * Bx:3 * Bx]), ptr(self.stats), main.cuda_stream)
-        if strat in (1, 2):  # dE += alpha (G + G^T) E
-            if fork:
+        if strat in (1, 2):  # dE += alpha (G + G^T) E: on the tensor-core path the product already sits in dE2 (mining branch)
+            if ev_mined is not None:
                 main.wait_event(ev_mined)
-            if tc:
-                if not fork:
-                    self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
-                            main.cuda_stream)
-                self._tc_gemm(B, H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE, H, k_splits=-1,
-                              accumulate=1, tag='gemm_dE_tri')
-            else:
+            if not tc:
                 self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
                 self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
         if par:
             self._fork(main, sideB)           # branch B: after the zeroing (already on sideB) and after dE / dE_tri were issued
             with torch.cuda.stream(sideB):
                 self._dW_gemm(B, accumulate=1)
-            main.wait_event(ev_zero)          # the sparse dW / dbh of the encode backward accumulate into the zeroed buffer
-        self._encode_backward(B, rows)
+        self._encode_backward(B, rows, dE_add=self.dE2 if (tc and strat in (1, 2)) else None, dbh_zeroed=1 if par else 0)
         if not fork:
             self._finalize(B, strat, weight, stats_log_row, main)
         elif stage_next is not None:          # tail of branch A, after the step's scalars
@@ -510,11 +605,23 @@ class TrainEngine:
                 self._stage_next_batch(stage_next[0], stage_next[1], B, sideA)
         if par:
             self._fork(sideB, main)
-        if sideA is not None and (fork or stage_next is not None):
+        if used_a:
             self._fork(sideA, main)           # join before the cursors advance / the next step reuses `stats`
         if getattr(self, '_defer_update', False):
             return
         self._apply_update()
+
+    def _dE_triplet(self, B, stream):
+        """dE2 = alpha (G + G^T) E, the triplet part of dL/dE; the encode backward adds it to the decode part (dE_add)."""
+        with torch.cuda.stream(stream):
+            if self.small_gemm == 'tc':
+                self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
+                        stream.cuda_stream)
+                self._tc_gemm(B, self.H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE2, self.H, tag='gemm_dE_tri')
+            else:   # G.E, then G^T.E on top (the transpose is a stride swap)
+                H = self.H
+                self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 0.0, self.dE2, H, tag='gemm_dE_tri')
+                self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE2, H, tag='gemm_dE_tri')
 
     def _finalize(self, B, strat, weight, stats_log_row, stream):
         self._k('dae_step_finalize', ptr(self.row_loss), None, 0, ptr(weight), B, strat, self.alpha, ptr(self.stats),
@@ -529,7 +636,7 @@ class TrainEngine:
     def _mining(self, B, strat, tc):
         """S = E.E^T and the triplet kernel (loss, statistics, G = dL/dS; batch_hard: also the data weights)."""
         H, st = self.H, _stream()
-        if tc:
+        if tc and self.small_gemm == 'tc':
             Ehl = (self.E_hi, self.E_lo)
             self._tc_gemm(B, B, H, 1.0, Ehl, 0, Ehl, 0, self.S, B, tag='gemm_gram')
         else:
@@ -564,6 +671,7 @@ class TrainEngine:
             self._ctl = None
             self._ensure_ws(3 * B)
             self._k('dae_batch_prepare_explicit', None, 0, None, B, B, ptr(self.rows), ptr(self.stats), _stream())
+            self._branch_b_prologue(3 * B, False)
             self._encode_forward(3 * B, False)
             self._train_tail(3 * B, 3, None, None, False, explicit_B=B)
             return self.read_stats()
@@ -583,7 +691,7 @@ class TrainEngine:
         self._gemm(F, H, B, 1.0, self.Z, 1, F, self.E, 1, H, 0.0, self._gW(), H, tag='gemm_decode_dW')  # dW_dec = dZ^T.E
         self._gemm(B, H, F, 1.0, self.Z, F, 1, self.W, 1, H, 0.0, self.dE, H, tag='gemm_decode_dE')    # dE = dZ.W
 
-    def _decode_tc(self, B, rows, weight, train=True):
+    def _decode_tc(self, B, rows, weight, train=True, prepared=0):
         """Decode forward + loss on the tensor cores (bf16x3):  Z = E.W^T with the loss epilogue fused (no Z / D / dense X in
         HBM); dZ leaves as the bf16 hi/lo pair the two backward GEMMs consume."""
         F, H, st = self.F, self.H, _stream()
@@ -592,8 +700,8 @@ class TrainEngine:
         if self.loss != 2:
             self._k('dae_decode_fused_bf16x3', B, F, H, ptr(self.E_hi), ptr(self.E_lo), self.Hp, ptr(self.W_hi), ptr(self.W_lo),
                     self.Hp, ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), ptr(self.bv), self.dec_act, self.loss,
-                    ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.row_loss), ptr(self.tile_ptr), st,
-                    n_launch=2, tag='gemm_decode_fwd')
+                    ptr(weight), ptr(self.stats), ptr(self.dZ_hi), ptr(self.dZ_lo), self.Fp, ptr(self.row_loss), ptr(self.tile_ptr),
+                    int(prepared), st, n_launch=1 if prepared else 2, tag='gemm_decode_fwd')
         else:  # cosine proximity needs whole-row norms before dZ: GEMM -> Z, elementwise loss, split
             self._tc_gemm(B, F, H, 1.0, Ehl, 0, Whl, 0, self.Z, F, tag='gemm_decode_fwd')
             self._k('dae_decode_loss_bwd', ptr(c.indptr), ptr(c.indices), ptr(c.values), ptr(rows), B, F, ptr(self.bv),
@@ -601,7 +709,7 @@ class TrainEngine:
             if train:
                 self._tc_split(self.Z, B, F, F, self.dZ_hi, self.dZ_lo)
 
-    def _encode_backward(self, B, rows):
+    def _encode_backward(self, B, rows, dE_add=None, dbh_zeroed=0):
         """K5: dA = dE * f'(A), dbh, and the sparse part of dW (X_c^T . dA) accumulated into the gradient buffer."""
         F, H, st = self.F, self.H, _stream()
         c = self.csr_c
@@ -609,13 +717,13 @@ class TrainEngine:
             scan_done = getattr(self, '_scan_done', False)
             self._scan_done = False
             self._k('dae_encode_csr_bwd_gather', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
-                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()),
+                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), ptr(dE_add), H, ptr(self._gW()), ptr(self._gbh()), int(dbh_zeroed),
                     None if scan_done else ptr(self.col_count),
                     ptr(self.col_start), ptr(self.col_cursor), ptr(self.ent_col), ptr(self.ent_row), ptr(self.ent_val), st, n_launch=3,
                     tag='dae_encode_csr_bwd')
         else:
             self._k('dae_encode_csr_bwd', ptr(c.indptr), ptr(c.indices), ptr(self.values_c), ptr(rows), B, F, H, self.in_scale,
-                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), H, ptr(self._gW()), ptr(self._gbh()), st)
+                    ptr(self.E), ptr(self.bh), self.enc_act, ptr(self.dE), ptr(dE_add), H, ptr(self._gW()), ptr(self._gbh()), int(dbh_zeroed), st)
 
     def _setup_multimem(self, n_blocks=148):
         """Move the gradient buffer into symmetric memory bound to a multicast address and create the peer-mapped flag words
@@ -664,17 +772,20 @@ class TrainEngine:
         self._ctl = ctl
         self._ensure_ws(B3)
         self._k('dae_batch_prepare_explicit', ptr(perm), int(offset), ptr(ctl), B, int(n_rows_each), ptr(self.rows), ptr(self.stats), _stream())
+        self._branch_b_prologue(B3, True)
         self._encode_forward(B3, True)
         self._train_tail(B3, 3, None, stats_log_row, True, explicit_B=B)
 
     # ---- transform ------------------------------------------------------------------------------------------------------
-    HOT_MIN_ROWS = 16384   # below this the per-launch staging of the hot rows (200 KB per SM) does not pay
+    HOT_MIN_ROWS = 16384   # below this the per-launch staging of the hot rows does not pay
+    HOT_BYTES = 200 * 1024  # staged set per CTA (the CTAs per SM follow from it)
+    HOT_GROUPS = 4          # row groups of 128 threads per CTA
 
     def _hot_columns(self, csr):
         """The K most frequent feature columns of `csr` (K rows of W fit 200 KB of shared memory) and the column -> slot table
         of dae_encode_csr_fwd_hot.  One histogram pass over the column ids; cached on the matrix."""
         hot = getattr(csr, '_hot', None)
-        K = min(self.F, (200 * 1024) // (self.H * 4))
+        K = max(1, min(self.F, self.HOT_BYTES // (self.H * 4)))
         if hot is None or hot[2] != K:
             counts = torch.bincount(csr.indices, minlength=self.F)
             cols = torch.topk(counts, K).indices.to(torch.int32)
@@ -698,7 +809,7 @@ class TrainEngine:
         if N >= self.HOT_MIN_ROWS and self.H % 4 == 0 and self.H <= 1024:
             cols, slot, K = self._hot_columns(csr)
             self._k('dae_encode_csr_fwd_hot', ptr(indptr), ptr(csr.indices), ptr(vals), N, self.F, self.H, float(in_scale), ptr(self.W),
-                    ptr(self.bh), self.enc_act, ptr(out), self.H, ptr(cols), ptr(slot), K, _stream(), tag='encode_transform')
+                    ptr(self.bh), self.enc_act, ptr(out), self.H, ptr(cols), ptr(slot), K, self.HOT_GROUPS, _stream(), tag='encode_transform')
         else:
             self._k('dae_encode_csr_fwd', ptr(indptr), ptr(csr.indices), ptr(vals), None, N, self.F, self.H, float(in_scale),
                     ptr(self.W), ptr(self.bh), self.enc_act, ptr(out), self.H, None, None, None, 0, _stream(), tag='encode_transform')

@@ -117,11 +117,14 @@ int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices, const floa
  * dA = dE * f'(A);  dbh = sum_i dA_i - f'(bh) * sum_i dE_i;  dW[c,:] += v * dA[r,:] for every stored
  * (r,c,v) of the corrupted batch (autodiff of autoencoder.py:389).  dE is overwritten with dA.
  * dW is accumulated with fp32 atomics on top of whatever the decode backward wrote.
+ * dE_add (optional, same layout as dE): a second contribution to dL/dE, added before f' is applied -- the triplet term
+ * alpha (G + G^T) E, computed on the mining branch of the step, meets the decode term here instead of in a GEMM of its own.
+ * dbh_zeroed != 0: the caller has already zeroed dbh (it zeroes the whole flat gradient buffer), skip the memset node.
  */
 int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const float* values,
                        const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
-                       const float* E, const float* bh, int32_t enc_act, float* dE, int64_t ldE,
-                       float* dW, float* dbh, void* stream);
+                       const float* E, const float* bh, int32_t enc_act, float* dE, const float* dE_add,
+                       int64_t ldE, float* dW, float* dbh, int32_t dbh_zeroed, void* stream);
 
 /* Same result with ~6x fewer atomics on dW: the batch's kept entries are bucketed by feature column (col_count from the
  * forward call; col_start int32[F+1], col_cursor int32[F], ent_col/ent_row int32[cap], ent_val f32[cap] are
@@ -134,18 +137,20 @@ int dae_encode_csr_bwd(const int64_t* indptr, const int32_t* indices, const floa
 int dae_col_scan(const int32_t* col_count, int32_t F, int32_t* col_start, int32_t* col_cursor, void* stream);
 int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* indices, const float* values,
                               const int32_t* rows, int32_t n_rows, int32_t F, int32_t H, float in_scale,
-                              const float* E, const float* bh, int32_t enc_act, float* dE, int64_t ldE, float* dW,
-                              float* dbh, const int32_t* col_count, int32_t* col_start, int32_t* col_cursor,
-                              int32_t* ent_col, int32_t* ent_row, float* ent_val, void* stream);
+                              const float* E, const float* bh, int32_t enc_act, float* dE, const float* dE_add,
+                              int64_t ldE, float* dW, float* dbh, int32_t dbh_zeroed, const int32_t* col_count,
+                              int32_t* col_start, int32_t* col_cursor, int32_t* ent_col, int32_t* ent_row,
+                              float* ent_val, void* stream);
 
 /* transform-sized K1 (many rows, one launch): persistent CTAs stage the K most frequent rows of W (hot_cols[K], 2 kB each at
  * H = 500) in shared memory with 1-D bulk-TMA copies and serve the entries of those columns from there; the cold tail gathers from
  * L2 as in dae_encode_csr_fwd.  hot_slot[F] = index of the column in hot_cols, or -1.  K * H * 4 <= 200 KB, H % 4 == 0.
+ * groups = 4 or 8 row groups of 128 threads per CTA; the number of CTAs per SM follows from the size of the staged set.
  * Same results as dae_encode_csr_fwd up to fp32 summation order inside a row (identical: entries are added in CSR order). */
 int dae_encode_csr_fwd_hot(const int64_t* indptr, const int32_t* indices, const float* values, int32_t n_rows,
                            int32_t F, int32_t H, float in_scale, const float* W, const float* bh, int32_t enc_act,
                            float* E, int64_t ldE, const int32_t* hot_cols, const int32_t* hot_slot, int32_t K,
-                           void* stream);
+                           int32_t groups, void* stream);
 
 /* ---- fp32 reference GEMM (CUDA cores) ----------------------------------------------------------
  * C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + beta * C[m,n]; generic strides.
@@ -184,15 +189,22 @@ int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_
                     int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
                     int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
                     float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
-/* Tile engine selection of the two entry points above (test hook): -1 = CTA pairs (cta_group::2: two SMs share one 256-row UMMA
- * tile, each staging half of the B operand) for the large GEMMs only -- the default --, 0 = never, 1 = whenever possible. */
-int dae_gemm_config(int32_t pair_mode);
+/* Tile engine selection of the two entry points above (test hook).  pair_mode: -1 = CTA pairs (cta_group::2: two SMs share one
+ * 256-row UMMA tile, each staging half of the B operand) for the large store GEMMs only -- the default --, 0 = never, 1 = whenever
+ * possible (fused decode included).  lean: 1 (default) = 2-stage operand rings (128 KB per CTA), which leave ~70 KB of every SM's
+ * shared memory to kernels running concurrently with the GEMM (the batch_all sweep, the CUDA-core mining GEMMs); 0 = deepest rings.
+ * tile_ptr of dae_decode_prepare is laid out for the configuration current at the time of the call. */
+int dae_gemm_config(int32_t pair_mode, int32_t lean);
+/* The part of the fused decode that needs only the batch's row ids: zero row_loss_part and fill tile_ptr.  dae_decode_fused_bf16x3
+ * runs it in line unless it is called with prepared != 0 (a graph-replayed step issues it on a parallel branch, next to K1). */
+int dae_decode_prepare(int32_t Brows, int32_t F, const int64_t* indptr, const int32_t* indices, const int32_t* rows,
+                       float* row_loss_part, int32_t* tile_ptr, void* stream);
 int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, const void* e_hi, const void* e_lo,
                             int64_t lde, const void* w_hi, const void* w_lo, int64_t ldw,
                             const int64_t* indptr, const int32_t* indices, const float* values,
                             const int32_t* rows, const float* bv, int32_t dec_act, int32_t loss_func,
                             const float* weight, const double* stats, void* dz_hi, void* dz_lo,
-                            int64_t ld_dz, float* row_loss_part, int32_t* tile_ptr, void* stream);
+                            int64_t ld_dz, float* row_loss_part, int32_t* tile_ptr, int32_t prepared, void* stream);
 /* out[i] = sum_p parts[p * n + i] (deterministic reduction of the per-tile row-loss partials) */
 int dae_reduce_parts(const float* parts, int32_t n_parts, int32_t n, float* out, void* stream);
 

@@ -12,7 +12,7 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
 
 
-def elem_err(a, b, floor=1e-2):
+def elem_err(a, b, floor=0.1):
     """Element-wise relative error: max_i |a_i - b_i| / max(|b_i|, floor * max|b|) -- every entry is compared with its OWN magnitude;
     entries below `floor` x the tensor's scale (results of cancellation) are compared with that floor instead."""
     a = np.asarray(a, dtype=np.float64)

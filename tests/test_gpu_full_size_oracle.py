@@ -41,9 +41,10 @@ def _check(eng, st, o, x_all, orc):
     emb = eng.encode(DeviceCSR(x_all, eng.device)).cpu().numpy()
     want = orc.transform(x_all)
     assert rel_err(emb, want) < REL_TOL
-    # element-wise: every embedding entry within 1e-4 of its OWN magnitude (entries below 1 % of the largest one -- f(A) - f(bh)
-    # cancelling -- are held to 1e-4 of that floor, i.e. 1e-6 of the scale)
-    assert elem_err(emb, want, floor=1e-2) < REL_TOL
+    # element-wise: every embedding entry within 1e-4 of its OWN magnitude; entries below 10 % of the largest one are held to 1e-4 of
+    # that floor (1e-5 of the scale): E = f(A) - f(bh) is a difference of two numbers near 0.5, so its fp32 value carries ~1e-7 of
+    # ABSOLUTE rounding noise in the reference's own arithmetic as well
+    assert elem_err(emb, want, floor=0.1) < REL_TOL, elem_err(emb, want, floor=0.1)
 
 
 @pytest.mark.parametrize('strategy,kind', [('batch_all', 'tfidf'), ('batch_hard', 'binary')])

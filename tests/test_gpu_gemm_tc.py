@@ -9,14 +9,15 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-@pytest.fixture(autouse=True, params=['auto', 'pair'])
+@pytest.fixture(autouse=True, params=['auto', 'pair', 'deep'])
 def _tile_engine(request):
-    """Every test runs twice: with the size-based choice between one-CTA tiles and CTA pairs (cta_group::2), and with the pairs
-    forced (small, ragged and single-m-tile shapes through the 2-SM kernel)."""
+    """Every test runs three times: with the default configuration (size-based choice between one-CTA tiles and CTA pairs, lean
+    2-stage rings), with the pairs forced (small, ragged and single-m-tile shapes through the cta_group::2 kernel), and with the
+    deepest operand rings (128 x 256 decode tiles, 3-stage pairs)."""
     from dae_rnn_news_recommendation_b200 import _cabi
-    _cabi.call('dae_gemm_config', 1 if request.param == 'pair' else -1)
+    _cabi.call('dae_gemm_config', 1 if request.param == 'pair' else -1, 0 if request.param == 'deep' else 1)
     yield
-    _cabi.call('dae_gemm_config', -1)
+    _cabi.call('dae_gemm_config', -1, 1)
 
 
 def _split(x, ld, ones_col=-1):
@@ -131,7 +132,7 @@ def test_fused_decode_matches_unfused(loss, dec, zscale):
     tptr = torch.empty(B, 4 * ((F + 255) // 256) + 1, dtype=torch.int32, device=DEV)
     _cabi.call('dae_decode_fused_bf16x3', B, F, H, Ehl[0].data_ptr(), Ehl[1].data_ptr(), Hp, Whl[0].data_ptr(), Whl[1].data_ptr(), Hp,
                csr.indptr.data_ptr(), csr.indices.data_ptr(), csr.values.data_ptr(), None, bv.data_ptr(), _cabi.ACT[dec],
-               _cabi.LOSS[loss], w.data_ptr(), stats.data_ptr(), dzh.data_ptr(), dzl.data_ptr(), Fp, parts.data_ptr(), tptr.data_ptr(), st)
+               _cabi.LOSS[loss], w.data_ptr(), stats.data_ptr(), dzh.data_ptr(), dzl.data_ptr(), Fp, parts.data_ptr(), tptr.data_ptr(), 0, st)
     rl2 = parts.view(-1)[:B]
     torch.cuda.synchronize()
     assert rel_err(rl2.cpu().numpy(), rl.cpu().numpy()) < 2e-5

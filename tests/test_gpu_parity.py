@@ -250,7 +250,7 @@ def test_triplet_estimator_fit(gemm_mode):
     W0 = xavier(F, 20, 64) * 3
     m = DenoisingAutoencoderTriplet(model_name='t', main_dir='t', compress_factor=10, enc_act_func='sigmoid', dec_act_func='sigmoid',
                                     loss_func='cross_entropy', num_epochs=3, batch_size=40.0, opt='gradient_descent', learning_rate=0.05,
-                                    corr_type='none', verbose=False, verbose_step=1, seed=5, alpha=2, W_init=W0)
+                                    corr_type='none', verbose=False, verbose_step=1, seed=5, alpha=2, W_init=W0, rng_mode='numpy')
     m.fit(data)
     assert len(m.train_cost_batch[0]) == 3 and np.isfinite(m.train_cost_batch[0]).all()
     emb = m.transform(data['org'])
@@ -265,7 +265,7 @@ def test_triplet_estimator_fit(gemm_mode):
     # first epoch's first step is the first row of the (last) epoch log only if num_epochs == 1 -> refit one epoch
     m1 = DenoisingAutoencoderTriplet(model_name='t1', main_dir='t1', compress_factor=10, enc_act_func='sigmoid', dec_act_func='sigmoid',
                                      loss_func='cross_entropy', num_epochs=1, batch_size=40.0, opt='gradient_descent', learning_rate=0.05,
-                                     corr_type='none', verbose=False, verbose_step=1, seed=5, alpha=2, W_init=W0)
+                                     corr_type='none', verbose=False, verbose_step=1, seed=5, alpha=2, W_init=W0, rng_mode='numpy')
     m1.fit(data)
     assert rel_err(m1.train_cost_batch[0][0], o['cost']) < REL_TOL
     assert rel_err(m1.train_cost_batch[2][0], o['triplet_loss']) < REL_TOL
@@ -292,3 +292,9 @@ def test_host_feed_graph_replay_matches_eager(gemm_mode, monkeypatch):
         res.append((costs, eng.get_parameters()['enc_w'], eng.step_count))
     assert res[0][2] == res[1][2] == steps
     assert rel_err(res[1][0], res[0][0]) < 1e-5 and rel_err(res[1][1], res[0][1]) < 1e-5
+    # streamed form (the next feed's H2D copy overlaps the current step, scalars through a pinned ring): same trajectory
+    eng = _engine(F, H, opt='momentum', learning_rate=0.05, triplet_strategy='batch_all')
+    eng.set_parameters(W0)
+    outs = eng.run_feeds([HostFeed(xb, xc, lb, cap_nnz=cap) for xb, xc, lb in batches])
+    assert len(outs) == steps and eng.step_count == steps
+    assert rel_err([o['cost'] for o in outs], res[1][0]) < 1e-6 and rel_err(eng.get_parameters()['enc_w'], res[1][1]) < 1e-6

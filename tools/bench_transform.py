@@ -30,8 +30,14 @@ for cfg in ('C2', 'C4'):
     distinct = int((torch.bincount(csr.indices, minlength=F) > 0).sum())
     alg = x.nnz * 8.0 + (N + 1) * 8.0 + distinct * H * 4.0 + H * 4.0 + N * H * 4.0
     gather = x.nnz * H * 4.0
-    for kern, min_rows in (('row', 1 << 30), ('hot', 1)):
-        eng.HOT_MIN_ROWS = min_rows
+    # row kernel, then the hot-rows kernel with (row groups per CTA, staged bytes per CTA -> CTAs per SM): 200 KB = 1 CTA/SM,
+    # 100 KB = 2, 64 KB = 3, 40 KB = 4
+    for kern, min_rows, groups, hot_bytes in (('row', 1 << 30, 4, 200), ('hot', 1, 4, 200), ('hot_g8', 1, 8, 200), ('hot_100k', 1, 4, 100),
+                                               ('hot_64k', 1, 4, 64), ('hot_40k', 1, 4, 40)):
+        eng.HOT_MIN_ROWS, eng.HOT_GROUPS, eng.HOT_BYTES = min_rows, groups, hot_bytes * 1024
+        if kern != 'row':
+            cols, slot, K = eng._hot_columns(csr)
+            hot_share = float((slot[csr.indices.long()] >= 0).float().mean())
         for _ in range(3):
             eng.encode(csr, in_scale=0.7, out=out)
         torch.cuda.synchronize()
@@ -42,9 +48,10 @@ for cfg in ('C2', 'C4'):
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
         res['%s_%s' % (cfg, kern)] = {
-            'kernel': 'dae_encode_csr_fwd' + ('_hot' if kern == 'hot' else ''), 'rows': N, 'F': F, 'H': H, 'ms': ms, 'rows_per_s': N / ms * 1e3,
+            'kernel': 'dae_encode_csr_fwd' + ('_hot' if kern != 'row' else ''), 'rows': N, 'F': F, 'H': H, 'ms': ms, 'rows_per_s': N / ms * 1e3,
             'algorithmic_bytes': alg, 'achieved_GBs': alg / ms / 1e6, 'hbm_peak_GBs': peaks['hbm_gbs'], 'frac_of_hbm': alg / ms / 1e6 / peaks['hbm_gbs'],
             'w_row_gather_bytes': gather, 'w_row_gather_GBs': gather / ms / 1e6, 'bytes_per_article': alg / N,
-            'hot_rows_K': K if kern == 'hot' else 0, 'entries_served_from_smem': hot_share if kern == 'hot' else 0.0}
+            'hot_rows_K': K if kern != 'row' else 0, 'entries_served_from_smem': hot_share if kern != 'row' else 0.0,
+            'row_groups_per_cta': groups if kern != 'row' else None}
     del eng, csr, out
 print(json.dumps(res))
