@@ -348,7 +348,7 @@ def main():
         eng.capture_step_graph(perm_buf, B, log, explicit_n=n_rows if explicit else None)   # one CUDA graph of the whole step
     launches0 = eng.launches
     clocks = Clocks(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get('DAE_BENCH_CLOCKS', '1') == '1':
         clocks.start()
         time.sleep(0.05)
     if world > 1:

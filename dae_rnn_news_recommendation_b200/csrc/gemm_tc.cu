@@ -818,7 +818,7 @@ static int sm_count() {
 }
 
 static int g_pair_mode = -1;   // -1: by size (dae_gemm_config); 0: never; 1: whenever the shape allows
-static int g_lean = 1;         // 1: leave ~70 KB of each SM's shared memory to concurrently running kernels (2-stage pipelines)
+static int g_lean = 0;         // 1: leave ~70 KB of each SM's shared memory to concurrently running kernels (2-stage pipelines)
 
 template <int BLOCK_N, int STAGES, int EPI, int ACT, int LOSS, int PAIR>
 static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStream_t st) {
@@ -999,8 +999,9 @@ extern "C" int dae_decode_fused_bf16x3(int32_t Brows, int32_t F, int32_t K, cons
   // measured at C2 (800 x 10000 x 500): the pair kernel's 3 rounds of 160 pair tiles on 74 SM pairs lose to 2 rounds of 280
   // single-CTA tiles (56 vs 47 us) -- the fused epilogue, not operand traffic, bounds this kernel; pairs only when forced (tests)
   const bool pair = (g_pair_mode == 1);
-  // lean: 128 x 128 tiles, 2 stages = 128 KB of operand ring instead of 192 KB (same speed: 39.4 vs 37.9 us standalone at C2), so that
-  // the batch_all sweep and the CUDA-core mining GEMMs can run on the same SMs while this kernel's tensor pipe works
+  // lean: 128 x 128 tiles, 2 stages = 128 KB of operand ring instead of 192 KB, so that other kernels can share the SM.  Measured at
+  // C2 (profiles/README.md): 51 vs 47.6 us standalone, and co-residency does not pay -- a sweep sharing SMs with the GEMMs slows both
+  // (shared-memory bandwidth is the tensor cores' operand path) -- so the deep rings are the default
 #define DAE_DEC(ACT, LOSS) rc = pair ? launch_gemm<256, 3, EPI_DECODE, ACT, LOSS, 1>(A, B, p, st) \
                               : (g_lean ? launch_gemm<128, 2, EPI_DECODE, ACT, LOSS, 0>(A, B, p, st) : launch_gemm<256, 2, EPI_DECODE, ACT, LOSS, 0>(A, B, p, st))
   if (loss_func == DAE_LOSS_CE) {

@@ -406,10 +406,14 @@ extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, con
   const int Pk = (B + kKTile - 1) / kKTile * kKTile;
   const size_t smem = sizeof(float) * ((size_t)3 * Pj + (size_t)2 * Pk + (size_t)kTY * Pk);
   DAE_REQUIRE(smem + 1024 <= 227 * 1024, "dae_triplet_batch_all: B=%d needs %zu B of shared memory", B, smem);
-  static size_t attr_smem = 0;  // opt in to > 48 KB of dynamic shared memory (grown monotonically)
-  if (smem > attr_smem) {
-    DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  {   // opt in to > 48 KB of dynamic shared memory: a per-DEVICE function attribute, remembered per device (grown monotonically)
+    static size_t attr_smem[64] = {0};
+    int dev = 0;
+    DAE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || smem > attr_smem[dev]) {
+      DAE_CUDA(cudaFuncSetAttribute(triplet_batch_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
+    }
   }
   triplet_batch_all_kernel<<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk, pos_only);
   DAE_CHECK_LAUNCH("dae_triplet_batch_all");

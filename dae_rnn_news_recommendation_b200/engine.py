@@ -472,7 +472,7 @@ class TrainEngine:
     def _branch_b_prologue(self, B, train):
         """Start of branch B, forked BEFORE K1: everything the later kernels need that depends on nothing but the batch's row ids --
         zero the gradient buffer (dense dW, sparse dW and dbh accumulate into it) and dE (its stream-K GEMM accumulates), and the
-        row-id part of the fused decode (row-loss zeroing, per-tile CSR offsets).  All of it runs next to K1, off the critical path."""
+        row-id part of the fused decode (row-loss zeroing, per-tile CSR offsets)."""
         self._branch_b = (0, None)
         if not (self.gemm_mode == 'tc' and train and self.fork_branches):
             return
@@ -480,13 +480,13 @@ class TrainEngine:
         self._fork(main, sideB)
         prepared = 0
         with torch.cuda.stream(sideB):
-            self.grad.zero_()
-            self.dE.zero_()
-            if self.loss != 2:
+            if self.loss != 2:   # first on the branch: it becomes runnable together with K1 (whose 800 CTAs then fill the machine)
                 c = self.csr
                 self._k('dae_decode_prepare', B, self.F, ptr(c.indptr), ptr(c.indices), ptr(self.rows), ptr(self.row_loss),
                         ptr(self.tile_ptr), sideB.cuda_stream)
                 prepared = 1
+            self.grad.zero_()
+            self.dE.zero_()
             ev = torch.cuda.Event()
             ev.record(sideB)
         self._branch_b = (prepared, ev)
@@ -533,9 +533,6 @@ class TrainEngine:
             used_a = True
             self._fork(main, sideA)
             with torch.cuda.stream(sideA):
-                if gather:   # the column-bucket offsets of the backward gather only need the forward kernel's counts
-                    self._k('dae_col_scan', ptr(self.col_count), F, ptr(self.col_start), ptr(self.col_cursor), sideA.cuda_stream)
-                    self._scan_done = True
                 self._mining(B, strat, tc)
                 self._dE_triplet(B, sideA)
                 ev_mined = torch.cuda.Event()
@@ -553,7 +550,14 @@ class TrainEngine:
         dec_prepared, ev_zero = 0, None
         if par:
             dec_prepared, ev_zero = self._branch_b
-            main.wait_event(ev_zero)              # zeroed gradient / dE buffers, decode row-id tables (issued before K1)
+            main.wait_event(ev_zero)              # zeroed gradient / dE buffers (issued before K1)
+            if gather:   # the column-bucket offsets of the backward gather only need K1's counts: branch B, far from any critical path
+                self._fork(main, sideB)
+                with torch.cuda.stream(sideB):
+                    self._k('dae_col_scan', ptr(self.col_count), F, ptr(self.col_start), ptr(self.col_cursor), sideB.cuda_stream)
+                    self._scan_done = True
+                    ev_scan = torch.cuda.Event()
+                    ev_scan.record(sideB)
         if stage_next is not None and not fork:   # (batch_hard) the staging buffers were consumed by dae_batch_commit: refill them now
             used_a = True
             self._fork(main, sideA)
@@ -597,6 +601,8 @@ class TrainEngine:
             self._fork(main, sideB)           # branch B: after the zeroing (already on sideB) and after dE / dE_tri were issued
             with torch.cuda.stream(sideB):
                 self._dW_gemm(B, accumulate=1)
+        if par and gather:
+            main.wait_event(ev_scan)
         self._encode_backward(B, rows, dE_add=self.dE2 if (tc and strat in (1, 2)) else None, dbh_zeroed=1 if par else 0)
         if not fork:
             self._finalize(B, strat, weight, stats_log_row, main)
@@ -777,9 +783,13 @@ class TrainEngine:
         self._train_tail(B3, 3, None, stats_log_row, True, explicit_B=B)
 
     # ---- transform ------------------------------------------------------------------------------------------------------
-    HOT_MIN_ROWS = 16384   # below this the per-launch staging of the hot rows does not pay
+    # dae_encode_csr_fwd_hot (hot rows of W staged in shared memory by bulk TMA) is OFF by default: measured on 100 k articles it cuts
+    # the L2 -> L1 gather traffic by 40 % but loses to the row-gather kernel (C2: 1.37 ms vs 1.14 ms, C4: 2.77 vs 1.86; every variant in
+    # profiles/r02_transform.json) -- the staged set costs the occupancy that hides the cold gathers' latency.  HOT_MIN_ROWS = N turns it on
+    # for launches of at least N rows.
+    HOT_MIN_ROWS = 1 << 62
     HOT_BYTES = 200 * 1024  # staged set per CTA (the CTAs per SM follow from it)
-    HOT_GROUPS = 4          # row groups of 128 threads per CTA
+    HOT_GROUPS = 8          # row groups of 128 threads per CTA
 
     def _hot_columns(self, csr):
         """The K most frequent feature columns of `csr` (K rows of W fit 200 KB of shared memory) and the column -> slot table
@@ -829,7 +839,7 @@ class TrainEngine:
         saved = (self.step_count, self.timed)
         self.timed = None
         n_perm = int(perm_buf.numel()) if perm_buf is not None else 0
-        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and perm_buf is not None
+        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and perm_buf is not None and os.environ.get('DAE_STAGE', '1') == '1'
         self._graph_meta = {'perm': perm_buf, 'B': B, 'staged': use_stage}
 
         def one_step():

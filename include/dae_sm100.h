@@ -191,8 +191,8 @@ int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_
                     float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
 /* Tile engine selection of the two entry points above (test hook).  pair_mode: -1 = CTA pairs (cta_group::2: two SMs share one
  * 256-row UMMA tile, each staging half of the B operand) for the large store GEMMs only -- the default --, 0 = never, 1 = whenever
- * possible (fused decode included).  lean: 1 (default) = 2-stage operand rings (128 KB per CTA), which leave ~70 KB of every SM's
- * shared memory to kernels running concurrently with the GEMM (the batch_all sweep, the CUDA-core mining GEMMs); 0 = deepest rings.
+ * possible (fused decode included).  lean: 0 (default) = deepest operand rings; 1 = 2-stage rings (128 KB per CTA), which leave
+ * ~70 KB of every SM's shared memory to kernels running concurrently with the GEMM.
  * tile_ptr of dae_decode_prepare is laid out for the configuration current at the time of the call. */
 int dae_gemm_config(int32_t pair_mode, int32_t lean);
 /* The part of the fused decode that needs only the batch's row ids: zero row_loss_part and fill tile_ptr.  dae_decode_fused_bf16x3

@@ -9,15 +9,15 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-@pytest.fixture(autouse=True, params=['auto', 'pair', 'deep'])
+@pytest.fixture(autouse=True, params=['auto', 'pair', 'lean'])
 def _tile_engine(request):
-    """Every test runs three times: with the default configuration (size-based choice between one-CTA tiles and CTA pairs, lean
-    2-stage rings), with the pairs forced (small, ragged and single-m-tile shapes through the cta_group::2 kernel), and with the
-    deepest operand rings (128 x 256 decode tiles, 3-stage pairs)."""
+    """Every test runs three times: with the default configuration (size-based choice between one-CTA tiles and CTA pairs, deepest
+    operand rings), with the pairs forced (small, ragged and single-m-tile shapes through the cta_group::2 kernel), and with the
+    lean 2-stage rings (128 x 128 decode tiles, 2-stage pairs)."""
     from dae_rnn_news_recommendation_b200 import _cabi
-    _cabi.call('dae_gemm_config', 1 if request.param == 'pair' else -1, 0 if request.param == 'deep' else 1)
+    _cabi.call('dae_gemm_config', 1 if request.param == 'pair' else -1, 1 if request.param == 'lean' else 0)
     yield
-    _cabi.call('dae_gemm_config', -1, 1)
+    _cabi.call('dae_gemm_config', -1, 0)
 
 
 def _split(x, ld, ones_col=-1):

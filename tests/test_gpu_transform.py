@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 
-@pytest.mark.parametrize('F,H,act', [(10000, 500, 'sigmoid'), (6000, 1000, 'tanh'), (3000, 52, 'none')])
-def test_hot_kernel_matches_row_kernel_and_oracle(F, H, act):
+@pytest.mark.parametrize('F,H,act,groups', [(10000, 500, 'sigmoid', 8), (6000, 1000, 'tanh', 4), (3000, 52, 'none', 8)])
+def test_hot_kernel_matches_row_kernel_and_oracle(F, H, act, groups):
     from oracle.dae_oracle import OracleDAE
     from dae_rnn_news_recommendation_b200.engine import TrainEngine, DeviceCSR
     from dae_rnn_news_recommendation_b200.synth import make_sparse
@@ -24,10 +24,9 @@ def test_hot_kernel_matches_row_kernel_and_oracle(F, H, act):
     eng = TrainEngine(F, H, enc_act_func=act, triplet_strategy='none', device=DEV)
     eng.set_parameters(W0, bh)
     csr = DeviceCSR(x, eng.device)
-    assert N >= eng.HOT_MIN_ROWS
+    row = eng.encode(csr, in_scale=0.7).cpu().numpy()                     # row-gather kernel (the default)
+    eng.HOT_MIN_ROWS, eng.HOT_GROUPS = 1, groups
     hot = eng.encode(csr, in_scale=0.7).cpu().numpy()                     # hot-rows kernel
-    eng.HOT_MIN_ROWS = 1 << 30
-    row = eng.encode(csr, in_scale=0.7).cpu().numpy()                     # row-gather kernel
     assert np.abs(hot - row).max() <= 1e-6 * np.abs(row).max()            # same products, same order inside a row
     sub = slice(0, 3000)
     orc = OracleDAE(W0, bh0=bh, enc_act_func=act, triplet_strategy='none')

@@ -12,12 +12,19 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import bench
 from dae_rnn_news_recommendation_b200.engine import TrainEngine, DeviceCSR
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument('N', nargs='?', type=int, default=100000)
+ap.add_argument('reps', nargs='?', type=int, default=10)
+ap.add_argument('--configs', default='C2,C4')
+ap.add_argument('--variants', default='row,hot,hot_g8,hot_100k,hot_64k,hot_40k')
+ap.add_argument('--warmup', type=int, default=3)
+args = ap.parse_args()
+N, reps = args.N, args.reps
 dev = torch.device('cuda:0')
 peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
 res = {}
-for cfg in ('C2', 'C4'):
+for cfg in args.configs.split(','):
     w = bench.CONFIGS[cfg]
     F, H = w['F'], w['H']
     x, _ = bench.make_data(w, N, 1)
@@ -34,11 +41,13 @@ for cfg in ('C2', 'C4'):
     # 100 KB = 2, 64 KB = 3, 40 KB = 4
     for kern, min_rows, groups, hot_bytes in (('row', 1 << 30, 4, 200), ('hot', 1, 4, 200), ('hot_g8', 1, 8, 200), ('hot_100k', 1, 4, 100),
                                                ('hot_64k', 1, 4, 64), ('hot_40k', 1, 4, 40)):
+        if kern not in args.variants.split(','):
+            continue
         eng.HOT_MIN_ROWS, eng.HOT_GROUPS, eng.HOT_BYTES = min_rows, groups, hot_bytes * 1024
         if kern != 'row':
             cols, slot, K = eng._hot_columns(csr)
             hot_share = float((slot[csr.indices.long()] >= 0).float().mean())
-        for _ in range(3):
+        for _ in range(args.warmup):
             eng.encode(csr, in_scale=0.7, out=out)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -41,7 +41,7 @@ ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUD
 ev.sort(key=lambda e: e.time_range.start)
 rows = [{'name': e.name[:60], 't0': e.time_range.start, 't1': e.time_range.end, 'stream': getattr(e, 'device_index', 0)} for e in ev]
 # split into steps at the first kernel of a step (the batch commit / prepare kernel)
-first = [i for i, r in enumerate(rows) if 'batch_commit' in r['name'] or ('batch_prepare' in r['name'] and 'next' not in r['name']) or 'batch_rows' in r['name']]
+first = [i for i, r in enumerate(rows) if 'batch_commit' in r['name'] or 'batch_rows' in r['name']]
 out = {'config': w['name'], 'n_events': len(rows), 'steps_found': len(first)}
 if len(first) >= 3:
     lo, hi = first[-2], first[-1]
