@@ -14,6 +14,7 @@ flat gradient per step).
 offline) on the host cores, same config.
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -160,8 +161,9 @@ def run_reference(args):
 class Clocks:
     REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.0005):
         self.index, self.samples, self.stop_flag, self.thr, self.h, self.err = index, [], False, None, None, None
+        self.period_s = period_s
 
     def start(self):
         try:
@@ -191,7 +193,7 @@ class Clocks:
             except Exception as e:   # noqa: BLE001
                 self.err = repr(e)
                 return
-            time.sleep(0.0005)
+            time.sleep(self.period_s)
 
     def stop(self, t0, t1):
         self.stop_flag = True
@@ -209,7 +211,7 @@ class Clocks:
                 if rs & bit:
                     reasons.add(name)
         return {'sm_mhz': float(np.median([s[1] for s in sel])), 'sm_max_mhz': self.max_sm, 'reasons': sorted(reasons),
-                'samples': len(sel), 'samples_inside_timed_region': inside, 'source': 'NVML polled every ~0.5 ms'}
+                'samples': len(sel), 'samples_inside_timed_region': inside, 'source': 'NVML polled every ~%g ms' % (self.period_s * 1e3)}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -347,14 +349,24 @@ def main():
     if use_graph:
         eng.capture_step_graph(perm_buf, B, log, explicit_n=n_rows if explicit else None)   # one CUDA graph of the whole step
     launches0 = eng.launches
-    clocks = Clocks(local)
-    if rank == 0 and os.environ.get('DAE_BENCH_CLOCKS', '1') == '1':
+    # multi-GPU: NVML calls from a process whose kernels talk to peer / multicast memory stall those kernels (measured at 2 GPUs with a
+    # 0.5 ms poll: 0.31 -> 0.47 ms per step with NCCL, 0.33 -> 1.4 ms with the in-switch exchange), so the poll is 10x coarser there
+    clocks = Clocks(local, period_s=0.0005 if world == 1 else 0.005)
+    if rank == 0:
         clocks.start()
         time.sleep(0.05)
+    # a generation-2 collection of the interpreter (torch + scipy keep ~1 M tracked objects alive: tens of ms) must not fall between
+    # two graph launches of a 5 ms timed region: collect now, then keep the collector off inside the timed regions
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # device time, not host hiccups: the K steps (and the epoch-start work) are enqueued BEHIND a ~15 ms spin kernel, so the events
+    # bracket back-to-back device execution even if a host thread (NVML poll, another rank's process) delays a launch call
+    torch.cuda._sleep(30_000_000)
     t_wall0 = time.time()
     e0.record()
     run(K, first, log=log, graph=use_graph)
@@ -488,6 +500,7 @@ def main():
             finally:
                 os.chdir(cwd)
 
+    gc.enable()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -511,7 +524,8 @@ def main():
                    'l2': 'inputs larger than L2: every step gathers %d fresh rows of the %.0f MB device-resident set (CSR + corrupted values) '
                          'and streams %.0f MB of parameter / gradient / operand state; L2 is 126 MB'
                          % (B * (3 if explicit else 1), set_mb, state_mb),
-                   'window': 'K steps from an epoch boundary: one corruption pass over the set and one permutation inside',
+                   'window': 'K steps from an epoch boundary: one corruption pass over the set and one permutation inside; CUDA events '
+                             'around the K steps, which are enqueued behind a 15 ms spin kernel (device time without host launch hiccups)',
                    'loss_first_last': [float(losses[0, 0]), float(losses[-1, 0])],
                    'launch': 'cuda graph replay' if use_graph else 'eager', 'grad_exchange': exchange},
         'clocks': clk,

@@ -85,8 +85,6 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if os.environ.get('DAE_GEMM_PAIR') or os.environ.get('DAE_GEMM_LEAN'):   # development switches of the tile engine (dae_gemm_config)
-            l.dae_gemm_config(int(os.environ.get('DAE_GEMM_PAIR', -1)), int(os.environ.get('DAE_GEMM_LEAN', 0)))
         _lib = l
     return _lib
 

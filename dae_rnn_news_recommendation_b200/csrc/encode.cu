@@ -564,8 +564,7 @@ extern "C" int dae_encode_csr_fwd(const int64_t* indptr, const int32_t* indices,
   dim3 grid(n_rows);
   // Few rows (a training batch): every row is resident at once and the launch lasts as long as its longest row -> split rows over
   // 4 thread groups.  Many rows (transform): throughput-bound, one group per row keeps more rows in flight.
-  static const int forced = getenv("DAE_ENC_GROUPS") ? atoi(getenv("DAE_ENC_GROUPS")) : 0;
-  const int groups = forced ? forced : (n_rows <= 148 * 32 ? 4 : 1);
+  const int groups = (n_rows <= 148 * 32) ? 4 : 1;
   DAE_DISPATCH_ACT(enc_act, ACT, {
     if (vw == 4) launch_fwd_nc<ACT, 4>(nc, groups, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);
     else if (vw == 2) launch_fwd_nc<ACT, 2>(nc, groups, grid, st, indptr, indices, values, rows, H, in_scale, W, bh, E, ldE, col_count, e_hi, e_lo, ld_split);

@@ -132,16 +132,16 @@ class TrainEngine:
         # dense contractions: 'tc' = tcgen05 bf16x3 kernels (production), 'ffma' = fp32 CUDA-core validation kernels
         self.gemm_mode = gemm or os.environ.get('DAE_GEMM', 'tc')
         assert self.gemm_mode in ('tc', 'ffma')
-        # the two SMALL contractions of the mining branch (S = E.E^T, dE2 = alpha (G + G^T) E; 0.64 GFLOP each): 'ffma' = the fp32
-        # CUDA-core kernel, which needs 17 KB of shared memory and runs NEXT TO the persistent tcgen05 CTAs of the decode chain;
-        # 'tc' = the tensor-core kernel, which has to wait for an SM's whole shared memory
-        self.small_gemm = os.environ.get('DAE_SMALL_GEMM', 'tc') if self.gemm_mode == 'tc' else 'ffma'
+        # the two SMALL contractions of the mining branch (S = E.E^T, dE2 = alpha (G + G^T) E; 0.64 GFLOP each) also run on the tensor
+        # cores: the fp32 CUDA-core kernel would co-reside with the persistent tcgen05 CTAs (17 KB of shared memory) but takes 50 / 79 us
+        # against 17 / 19 us (measured at C2)
+        self.small_gemm = self.gemm_mode
         # encode backward: 'gather' = column-bucketed, atomic-free dW accumulation; 'atomic' = red.global.add per entry
-        self.enc_bwd_mode = os.environ.get('DAE_ENC_BWD', 'gather')
+        self.enc_bwd_mode = 'gather'
         if self.H > (1024 if self.H % 4 == 0 else (512 if self.H % 2 == 0 else 256)):
             self.enc_bwd_mode = 'atomic'
         self._ent_cap = 0
-        self.fork_branches = os.environ.get('DAE_FORK', '1') == '1'
+        self.fork_branches = True   # parallel branches of the step (False: one stream, what the per-kernel timing pass uses)
         self._sides = [None, None]
         self.Hp = (self.H + 1 + 63) // 64 * 64   # K padding of E / W (+1: the all-ones column that turns dW into [dW | dbv])
         self.Fp = (self.F + 31) // 32 * 32
@@ -153,10 +153,11 @@ class TrainEngine:
         self._graph2 = None
         self._ctl_owner = None
         self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
-        # gradient exchange of the data-parallel step: 'nccl' = eager ncclAllReduce between two captured graphs, 'nccl_graph' = the
-        # NCCL all-reduce captured inside the step's graph, 'multimem' = in-switch reduction by dae_allreduce_multimem (a plain
-        # kernel, captured inside the step's graph; needs NVSwitch multicast)
-        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'auto')) if self.world > 1 else 'none'
+        # gradient exchange of the data-parallel step: 'nccl_graph' (default) = the NCCL all-reduce captured inside the step's graph;
+        # 'multimem' = in-switch reduction by dae_allreduce_multimem (a plain kernel, captured inside the step's graph; needs NVSwitch
+        # multicast); 'auto' = multimem where the multicast rendezvous succeeds, else nccl_graph; 'nccl' = the round-1 scheme, an
+        # eager ncclAllReduce between two captured graphs.  Measured at 2 GPUs (C2): 0.312 / 0.326 / 0.311 ms per step.
+        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'nccl_graph')) if self.world > 1 else 'none'
         assert self.allreduce_mode in ('none', 'auto', 'nccl', 'nccl_graph', 'multimem')
         if self.allreduce_mode == 'auto':      # in-switch exchange where the fabric offers multicast, NCCL inside the graph otherwise
             try:
@@ -610,12 +611,16 @@ class TrainEngine:
             with torch.cuda.stream(sideA):
                 self._stage_next_batch(stage_next[0], stage_next[1], B, sideA)
         if par:
-            self._fork(sideB, main)
-        if used_a:
-            self._fork(sideA, main)           # join before the cursors advance / the next step reuses `stats`
+            self._fork(sideB, main)           # the dense dW / dbv are in the gradient buffer
         if getattr(self, '_defer_update', False):
+            if used_a:
+                self._fork(sideA, main)
             return
+        # branch A's tail (the step's scalars, the NEXT batch's staging: a 1-CTA sort that only gets an SM once a GEMM CTA retires)
+        # does not feed the update: it joins after the optimizer, before the cursors advance / the next step reuses `stats`
         self._apply_update()
+        if used_a:
+            self._fork(sideA, main)
 
     def _dE_triplet(self, B, stream):
         """dE2 = alpha (G + G^T) E, the triplet part of dL/dE; the encode backward adds it to the decode part (dE_add)."""
@@ -839,7 +844,7 @@ class TrainEngine:
         saved = (self.step_count, self.timed)
         self.timed = None
         n_perm = int(perm_buf.numel()) if perm_buf is not None else 0
-        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and perm_buf is not None and os.environ.get('DAE_STAGE', '1') == '1'
+        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and perm_buf is not None
         self._graph_meta = {'perm': perm_buf, 'B': B, 'staged': use_stage}
 
         def one_step():
@@ -897,7 +902,13 @@ class TrainEngine:
     def set_step_cursor(self, offset, log_row=0):
         """Host-side (re)positioning of the device cursors, e.g. at an epoch start."""
         self._ctl_owner = 'fit'
-        self.ctl.copy_(torch.tensor([int(offset), int(log_row), self.step_count + 1, 0], dtype=torch.int64), non_blocking=False)
+        if getattr(self, '_ctl_host', None) is None:
+            self._ctl_host = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(8)]   # ring: the copies are asynchronous
+            self._ctl_host_i = 0
+        h = self._ctl_host[self._ctl_host_i % len(self._ctl_host)]
+        self._ctl_host_i += 1
+        h[0], h[1], h[2], h[3] = int(offset), int(log_row), self.step_count + 1, 0
+        self.ctl.copy_(h, non_blocking=True)
         m = getattr(self, '_graph_meta', None)
         if m is not None and m['staged']:      # the replayed step takes its batch from the staging buffers
             self.stage_batch(m['perm'], int(offset), m['B'])
