@@ -350,8 +350,9 @@ def main():
         eng.capture_step_graph(perm_buf, B, log, explicit_n=n_rows if explicit else None)   # one CUDA graph of the whole step
     launches0 = eng.launches
     # multi-GPU: NVML calls from a process whose kernels talk to peer / multicast memory stall those kernels (measured at 2 GPUs with a
-    # 0.5 ms poll: 0.31 -> 0.47 ms per step with NCCL, 0.33 -> 1.4 ms with the in-switch exchange), so the poll is 10x coarser there
-    clocks = Clocks(local, period_s=0.0005 if world == 1 else 0.005)
+    # 0.5 ms poll: 0.31 -> 0.47 ms per step with NCCL, 0.33 -> 1.4 ms with the in-switch exchange; at 8 GPUs a 5 ms poll still cost NCCL
+    # 0.38 -> 0.99 ms), so the poll is 20x coarser there: the samples fall into the spin kernel that precedes the steps and into the steps
+    clocks = Clocks(local, period_s=0.0005 if world == 1 else 0.01)
     if rank == 0:
         clocks.start()
         time.sleep(0.05)

@@ -58,7 +58,7 @@ _SIGNATURES = {
     'dae_row_argmax': (C.c_int, [p, i32, i32, i64, i64, i32, p, p, p]),
     'dae_pair_partition': (C.c_int, [p, i64, i32, p, p, p, p, p]),
     'dae_auroc_count': (C.c_int, [p, i64, p, i64, i32, p, p]),
-    'dae_allreduce_multimem': (C.c_int, [p, p, i32, i32, i64, i32, p]),
+    'dae_allreduce_multimem': (C.c_int, [p, p, p, i32, i32, i64, i32, p]),
     'dae_mask_values': (C.c_int, [p, p, i64, f32, u64, u64, p, p]),
 }
 

@@ -10,21 +10,20 @@
 //
 // Per GPU that is N(P-1)/P bytes out and in over NVLink, no staging buffer, no intermediate HBM round trip, and -- being an
 // ordinary kernel on the step's stream -- it is captured inside the step's CUDA graph (NCCL's launch has to stay outside).
-// Barriers are per CTA: CTA b of rank r raises flag[b][r] on every peer and waits for its own flag[b][0..P-1]; a flag is a 0/1 word
-// that the waiter resets, so no epoch counter has to be kept in step with graph replays.
+// Barriers are per CTA: CTA b of rank r writes the exchange's epoch into flag[b][r] on every peer (one remote store each) and polls its
+// own flag[b][0..P-1] in local memory; the epoch is a per-CTA device counter the kernel advances itself, so it stays in step with graph
+// replays.
 #include "common.cuh"
 
 namespace dae {
 
-__device__ __forceinline__ unsigned cas_release_sys(unsigned* addr, unsigned expect, unsigned value) {
-  unsigned old;
-  asm volatile("atom.release.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(expect), "r"(value) : "memory");
-  return old;
+__device__ __forceinline__ void st_release_sys(unsigned* addr, unsigned value) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(value) : "memory");
 }
-__device__ __forceinline__ unsigned cas_acquire_sys(unsigned* addr, unsigned expect, unsigned value) {
-  unsigned old;
-  asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(addr), "r"(expect), "r"(value) : "memory");
-  return old;
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* addr) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ unsigned long long now_ns() {
@@ -36,24 +35,27 @@ __device__ __forceinline__ unsigned long long now_ns() {
 // and the error surfaces on the host at the next synchronisation.
 constexpr unsigned long long kBarrierTimeoutNs = 5000000000ull;
 
-// flags[p] = base of rank p's flag words (peer-mapped); word index = (phase * n_blocks + block) * world + source rank
-__device__ __forceinline__ void peer_barrier(unsigned* const* flags, int rank, int world, int phase) {
+// flags[p] = base of rank p's flag words (peer-mapped); word index = (phase * n_blocks + block) * world + source rank.
+// A flag carries the EPOCH of the exchange (a per-CTA counter kept in local memory and advanced by the kernel itself, so it stays in
+// step with graph replays): arriving is ONE fire-and-forget remote store per peer, waiting polls local memory -- no read-modify-write
+// round trips over NVLink and nothing to re-arm.
+__device__ __forceinline__ void peer_barrier(unsigned* const* flags, int rank, int world, int phase, unsigned epoch) {
   __syncthreads();
   if ((int)threadIdx.x < world) {
     const int64_t slot = ((int64_t)phase * gridDim.x + blockIdx.x) * world;
     __threadfence_system();
-    unsigned* remote = flags[threadIdx.x] + slot + rank;          // "rank `rank`, CTA b has arrived" on peer threadIdx.x
+    st_release_sys(flags[threadIdx.x] + slot + rank, epoch);      // "rank `rank`, CTA b has reached `epoch`" on peer threadIdx.x
+    const unsigned* mine = flags[rank] + slot + threadIdx.x;       // wait for peer threadIdx.x's CTA b
     const unsigned long long t0 = now_ns();
-    while (cas_release_sys(remote, 0u, 1u) != 0u) { if (now_ns() - t0 > kBarrierTimeoutNs) __trap(); }
-    unsigned* mine = flags[rank] + slot + threadIdx.x;            // wait for peer threadIdx.x's CTA b, then re-arm the word
-    while (cas_acquire_sys(mine, 1u, 0u) != 1u) { if (now_ns() - t0 > kBarrierTimeoutNs) __trap(); }
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) { if (now_ns() - t0 > kBarrierTimeoutNs) __trap(); }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(512) allreduce_multimem_kernel(float* __restrict__ mc, unsigned* const* __restrict__ flags, int rank, int world,
-                                                                 int64_t n) {
-  peer_barrier(flags, rank, world, 0);
+__global__ void __launch_bounds__(512) allreduce_multimem_kernel(float* __restrict__ mc, unsigned* const* __restrict__ flags,
+                                                                 unsigned* __restrict__ epochs, int rank, int world, int64_t n) {
+  const unsigned epoch = epochs[blockIdx.x] + 1u;     // every rank runs the same sequence of exchanges: the counters agree
+  peer_barrier(flags, rank, world, 0, epoch);
   const int64_t n4 = n >> 2;                                 // whole float4 packets; the <= 3 trailing floats go to rank 0
   const int64_t per = (n4 + world - 1) / world;
   const int64_t lo = (int64_t)rank * per;
@@ -85,18 +87,19 @@ __global__ void __launch_bounds__(512) allreduce_multimem_kernel(float* __restri
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(a) : "l"(p) : "memory");
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
   }
-  peer_barrier(flags, rank, world, 1);
+  peer_barrier(flags, rank, world, 1, epoch);
+  if (threadIdx.x == 0) epochs[blockIdx.x] = epoch;
 }
 
 }  // namespace dae
 
-extern "C" int dae_allreduce_multimem(float* multicast_grad, void* const* peer_flags, int32_t rank, int32_t world, int64_t n,
-                                      int32_t n_blocks, void* stream) {
+extern "C" int dae_allreduce_multimem(float* multicast_grad, void* const* peer_flags, uint32_t* epochs, int32_t rank, int32_t world,
+                                      int64_t n, int32_t n_blocks, void* stream) {
   using namespace dae;
-  DAE_REQUIRE(multicast_grad && peer_flags && world >= 2 && world <= 32 && rank >= 0 && rank < world && n > 0 && n_blocks > 0 && n_blocks <= 1024,
+  DAE_REQUIRE(multicast_grad && peer_flags && epochs && world >= 2 && world <= 32 && rank >= 0 && rank < world && n > 0 && n_blocks > 0 && n_blocks <= 1024,
               "dae_allreduce_multimem: bad arguments (world=%d rank=%d n=%lld blocks=%d)", world, rank, (long long)n, n_blocks);
   DAE_REQUIRE((reinterpret_cast<uintptr_t>(multicast_grad) & 15) == 0, "dae_allreduce_multimem: the multicast buffer must be 16-byte aligned");
-  allreduce_multimem_kernel<<<n_blocks, 512, 0, (cudaStream_t)stream>>>(multicast_grad, (unsigned* const*)peer_flags, rank, world, n);
+  allreduce_multimem_kernel<<<n_blocks, 512, 0, (cudaStream_t)stream>>>(multicast_grad, (unsigned* const*)peer_flags, epochs, rank, world, n);
   DAE_CHECK_LAUNCH("dae_allreduce_multimem");
   return DAE_OK;
 }

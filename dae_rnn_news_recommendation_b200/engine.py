@@ -153,11 +153,12 @@ class TrainEngine:
         self._graph2 = None
         self._ctl_owner = None
         self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
-        # gradient exchange of the data-parallel step: 'nccl_graph' (default) = the NCCL all-reduce captured inside the step's graph;
-        # 'multimem' = in-switch reduction by dae_allreduce_multimem (a plain kernel, captured inside the step's graph; needs NVSwitch
-        # multicast); 'auto' = multimem where the multicast rendezvous succeeds, else nccl_graph; 'nccl' = the round-1 scheme, an
-        # eager ncclAllReduce between two captured graphs.  Measured at 2 GPUs (C2): 0.312 / 0.326 / 0.311 ms per step.
-        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'nccl_graph')) if self.world > 1 else 'none'
+        # gradient exchange of the data-parallel step: 'multimem' = in-switch reduction by dae_allreduce_multimem (a plain kernel,
+        # captured inside the step's graph; needs NVSwitch multicast); 'nccl_graph' = the NCCL all-reduce captured inside the step's
+        # graph; 'auto' (default) = multimem where the multicast rendezvous succeeds on every rank, else nccl_graph; 'nccl' = the
+        # round-1 scheme, an eager ncclAllReduce between two captured graphs.  Measured (C2, ms per step): 2 GPUs 0.326 / 0.312 /
+        # 0.311, 8 GPUs 0.352 (multimem) / 0.377+ (nccl_graph).
+        self.allreduce_mode = (allreduce or os.environ.get('DAE_ALLREDUCE', 'auto')) if self.world > 1 else 'none'
         assert self.allreduce_mode in ('none', 'auto', 'nccl', 'nccl_graph', 'multimem')
         if self.allreduce_mode == 'auto':      # in-switch exchange where the fabric offers multicast, NCCL inside the graph otherwise
             try:
@@ -751,6 +752,7 @@ class TrainEngine:
         h_flags = symm.rendezvous(flags, group)
         self.grad = grad
         self._mm = {'grad': h_grad, 'flags': h_flags, 'flag_buf': flags, 'mc_ptr': int(h_grad.multicast_ptr),
+                    'epochs': torch.zeros(n_blocks, dtype=torch.int32, device=self.device),
                     'flag_ptrs': int(h_flags.buffer_ptrs_dev), 'rank': int(h_grad.rank), 'blocks': int(n_blocks)}
         torch.cuda.synchronize(self.device)
         torch.distributed.barrier(group)   # every rank's flag words are zero before the first exchange
@@ -758,7 +760,7 @@ class TrainEngine:
     def _allreduce_grad(self):
         if self.allreduce_mode == 'multimem':
             m = self._mm
-            self._k('dae_allreduce_multimem', m['mc_ptr'], m['flag_ptrs'], m['rank'], self.world, self.n_params, m['blocks'], _stream())
+            self._k('dae_allreduce_multimem', m['mc_ptr'], m['flag_ptrs'], ptr(m['epochs']), m['rank'], self.world, self.n_params, m['blocks'], _stream())
         else:
             torch.distributed.all_reduce(self.grad, group=self.pg)
 

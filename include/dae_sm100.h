@@ -301,13 +301,16 @@ int dae_auroc_count(const float* queries, int64_t n_queries, const float* sorted
  * gradient kernels and dae_optimizer_step.  Default transport: ncclAllReduce.  dae_allreduce_multimem is the
  * in-graph alternative: `multicast_grad` is the NVSwitch multicast address bound to every rank's gradient buffer
  * (symmetric memory, identical offset on every rank, n floats, 16-byte aligned); `peer_flags` is a DEVICE array of
- * `world` pointers to each rank's flag words (2 * n_blocks * world zero-initialised uint32, peer-mapped).  Every
- * rank calls it with the same n and n_blocks on its step stream; on return (stream order) every rank's buffer
- * holds the sum.  Rank r reduces float4 packets [r*ceil(n4/P), ...) with multimem.ld_reduce and writes them back
- * with multimem.st; CTA-level flag barriers open and close the exchange.
+ * `world` pointers to each rank's flag words (2 * n_blocks * world zero-initialised uint32, peer-mapped); `epochs` is
+ * this rank's own uint32[n_blocks] (zero-initialised, ordinary device memory): the per-CTA exchange counter the
+ * flags carry, advanced by the kernel itself so that it stays in step with CUDA-graph replays.  Every rank calls it
+ * with the same n and n_blocks on its step stream, the same number of times; on return (stream order) every rank's
+ * buffer holds the sum.  Rank r reduces float4 packets [r*ceil(n4/P), ...) with multimem.ld_reduce and writes them
+ * back with multimem.st; CTA-level flag barriers (one remote store per peer to arrive, local polling to wait) open and
+ * close the exchange and trap after 5 s instead of hanging a replica.
  */
-int dae_allreduce_multimem(float* multicast_grad, void* const* peer_flags, int32_t rank, int32_t world, int64_t n,
-                           int32_t n_blocks, void* stream);
+int dae_allreduce_multimem(float* multicast_grad, void* const* peer_flags, uint32_t* epochs, int32_t rank,
+                           int32_t world, int64_t n, int32_t n_blocks, void* stream);
 
 #ifdef __cplusplus
 }
