@@ -49,7 +49,8 @@ _SIGNATURES = {
     'dae_reduce_parts': (C.c_int, [p, i32, i32, p, p]),
     'dae_decode_loss_bwd': (C.c_int, [p, p, p, p, i32, i32, p, i32, i32, p, p, p, i64, p, p]),
     'dae_colsum': (C.c_int, [p, i32, i32, i64, p, p]),
-    'dae_triplet_batch_all': (C.c_int, [p, i64, i32, p, p, p, i64, p, i32, p]),
+    'dae_triplet_batch_all': (C.c_int, [p, i64, i32, p, p, p, i64, p, i32, p, p, i64, p]),
+    'dae_gemm_sym_bf16x3': (C.c_int, [i32, i32, f32, p, p, i64, p, p, i64, p, i64, i32, p]),
     'dae_triplet_batch_hard': (C.c_int, [p, i64, i32, p, p, i64, p, p, p]),
     'dae_triplet_explicit': (C.c_int, [p, p, p, i32, i32, i64, f32, p, p, p, p, p]),
     'dae_step_finalize': (C.c_int, [p, p, i32, p, i32, i32, f32, p, p, p, p]),

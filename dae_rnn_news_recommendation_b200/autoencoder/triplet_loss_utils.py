@@ -53,7 +53,7 @@ def batch_all_triplet_loss(sparse_input, input_label, encode, pos_triplets_only=
     S = _gram(E)
     G = torch.empty(B, B, device=_DEV)
     call('dae_triplet_batch_all', S.data_ptr(), B, B, lo.data_ptr(), hi.data_ptr(), G.data_ptr(), B, stats.data_ptr(),
-         1 if pos_triplets_only else 0, _stream())
+         1 if pos_triplets_only else 0, None, None, 0, _stream())
     torch.cuda.synchronize()
     st = stats.cpu().numpy()
     n_valid, n_pos, tsum = st[STAT['n_valid']], st[STAT['num']], st[STAT['triplet_sum']]

@@ -346,55 +346,44 @@ __global__ void __launch_bounds__(1024) col_scan_kernel(const int32_t* __restric
   if (tid == 0) col_start[F] = s_carry;
 }
 
-// per batch row: dA = dE * f'(A), dbh, and the row's kept entries appended to their column buckets.  A CTA takes kRowsPerCta rows
-// and keeps its dbh partial sums in registers: one atomic per hidden unit per CTA instead of one per (row, hidden unit) -- the H
-// addresses of dbh are otherwise hit by every row of the batch.
-constexpr int kRowsPerCta = 1;   // measured at B = 800: 1 row per CTA 14 us, 4 rows per CTA 19.6 us (fewer CTAs in flight)
+// per batch row: dA = dE * f'(A), dbh, and the row's kept entries appended to their column buckets.  One WARP per row, kRowsPerCta rows
+// per CTA: the rows' dbh contributions are summed through shared memory and leave as one atomic per hidden unit per CTA (the H
+// addresses of dbh are otherwise hit by every row of the batch), while the rows still progress in parallel.
+constexpr int kRowsPerCta = 4;
 
 template <int ACT>
-__global__ void __launch_bounds__(kEncThreads) encode_bwd_rows_kernel(
+__global__ void __launch_bounds__(32 * kRowsPerCta) encode_bwd_rows_kernel(
     const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
     const int32_t* __restrict__ rows, int n_rows, int H, float in_scale, const float* __restrict__ E, const float* __restrict__ bh,
     float* __restrict__ dE, const float* __restrict__ dE_add, int64_t ldE, float* __restrict__ dbh, int32_t* __restrict__ col_cursor, int32_t* __restrict__ ent_col,
     int32_t* __restrict__ ent_row, float* __restrict__ ent_val) {
-  constexpr int kMaxPer = 8;   // H <= 8 * 128 on this path
-  const int tid = threadIdx.x;
-  const int r0 = blockIdx.x * kRowsPerCta;
-  float fb[kMaxPer], gfb[kMaxPer], part[kMaxPer];
-#pragma unroll
-  for (int k = 0; k < kMaxPer; ++k) {
-    const int h = tid + k * kEncThreads;
-    const float b = (h < H) ? __ldg(bh + h) : 0.0f;
-    fb[k] = act_fwd<ACT>(b);
-    gfb[k] = act_grad_from_y<ACT>(fb[k]);
-    part[k] = 0.0f;
-  }
-  for (int rr = 0; rr < kRowsPerCta; ++rr) {
-    const int r = r0 + rr;
-    if (r >= n_rows) break;
-#pragma unroll
-    for (int k = 0; k < kMaxPer; ++k) {
-      const int h = tid + k * kEncThreads;
-      if (h < H) {
-        const float fa = E[(int64_t)r * ldE + h] + fb[k];
-        const float de = dE[(int64_t)r * ldE + h] + (dE_add ? dE_add[(int64_t)r * ldE + h] : 0.0f);
-        const float da = de * act_grad_from_y<ACT>(fa);
-        dE[(int64_t)r * ldE + h] = da;
-        part[k] += da - gfb[k] * de;
-      }
+  extern __shared__ float s_part[];   // [kRowsPerCta][H]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = blockIdx.x * kRowsPerCta + warp;
+  float* part = s_part + (int64_t)warp * H;
+  if (r < n_rows) {
+    for (int h = lane; h < H; h += 32) {
+      const float fb = act_fwd<ACT>(__ldg(bh + h));
+      const float fa = E[(int64_t)r * ldE + h] + fb;
+      const float de = dE[(int64_t)r * ldE + h] + (dE_add ? dE_add[(int64_t)r * ldE + h] : 0.0f);
+      const float da = de * act_grad_from_y<ACT>(fa);
+      dE[(int64_t)r * ldE + h] = da;
+      part[h] = da - act_grad_from_y<ACT>(fb) * de;
     }
+  } else {
+    for (int h = lane; h < H; h += 32) part[h] = 0.0f;
   }
+  __syncthreads();
+  for (int h = tid; h < H; h += 32 * kRowsPerCta) {
+    float t = 0.0f;
 #pragma unroll
-  for (int k = 0; k < kMaxPer; ++k) {
-    const int h = tid + k * kEncThreads;
-    if (h < H) atomicAdd(dbh + h, part[k]);
+    for (int w = 0; w < kRowsPerCta; ++w) t += s_part[(int64_t)w * H + h];
+    atomicAdd(dbh + h, t);
   }
-  for (int rr = 0; rr < kRowsPerCta; ++rr) {
-    const int r = r0 + rr;
-    if (r >= n_rows) break;
+  if (r < n_rows) {
     const int64_t row = rows ? (int64_t)rows[r] : (int64_t)r;
     const int64_t p0 = indptr[row], p1 = indptr[row + 1];
-    for (int64_t p = p0 + tid; p < p1; p += kEncThreads) {
+    for (int64_t p = p0 + lane; p < p1; p += 32) {
       const float v = __ldg(values + p) * in_scale;
       if (v != 0.0f) {
         const int col = __ldg(indices + p);
@@ -615,7 +604,7 @@ extern "C" int dae_encode_csr_bwd_gather(const int64_t* indptr, const int32_t* i
   if (nc < 0 || nc > 2) { set_error("dae_encode_csr_bwd_gather: H=%d not supported (use dae_encode_csr_bwd)", H); return DAE_ERR_UNSUPPORTED; }
   if (col_count) col_scan_kernel<<<1, 1024, 0, st>>>(col_count, F, col_start, col_cursor);  // NULL: dae_col_scan already ran
   DAE_DISPATCH_ACT(enc_act, ACT, {
-    encode_bwd_rows_kernel<ACT><<<(n_rows + kRowsPerCta - 1) / kRowsPerCta, kEncThreads, 0, st>>>(indptr, indices, values, rows, n_rows, H, in_scale, E, bh, dE, dE_add, ldE, dbh, col_cursor,
+    encode_bwd_rows_kernel<ACT><<<(n_rows + kRowsPerCta - 1) / kRowsPerCta, 32 * kRowsPerCta, sizeof(float) * kRowsPerCta * H, st>>>(indptr, indices, values, rows, n_rows, H, in_scale, E, bh, dE, dE_add, ldE, dbh, col_cursor,
                                                                ent_col, ent_row, ent_val);
   });
 #define DAE_GATHER(VW, NC) encode_bwd_gather_kernel<VW, NC><<<148 * 16, kEncThreads, 0, st>>>(col_start, F, ent_col, ent_row, ent_val, H, dE, ldE, dW)

@@ -190,6 +190,8 @@ struct GemmParams {
   int stream_k;          // 1: stream-K -- the CTAs share the (tile, k-block) units evenly, partial tiles are added with atomics
   int atomic;            // accumulate into C with fp32 atomics (split-K / stream-K, or C += ...)
   int a_mn, b_mn;        // operand majorness
+  int a_sym_kb;          // > 0: C = (A + A^T).B -- k-blocks [0, a_sym_kb) read the square A K-major, k-blocks [a_sym_kb, 2 a_sym_kb) read it
+                         // MN-major (= A^T) through the second pair of tensor maps, and B's k index wraps (both halves multiply B)
   float alpha;
   float* C;              // EPI_STORE: fp32 output [M x ldc]
   int64_t ldc;
@@ -360,6 +362,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
                                                                       const __grid_constant__ CUtensorMap tm_a_lo,
                                                                       const __grid_constant__ CUtensorMap tm_b_hi,
                                                                       const __grid_constant__ CUtensorMap tm_b_lo,
+                                                                      const __grid_constant__ CUtensorMap tm_at_hi,   // A^T views (a_sym_kb > 0)
+                                                                      const __grid_constant__ CUtensorMap tm_at_lo,
                                                                       const GemmParams p) {
   constexpr int A_TILE = BLOCK_M * BLOCK_K * 2;   // bytes of one bf16 A tile (16 KB)
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;   // n rows of the B tile staged by this CTA
@@ -385,6 +389,7 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
+    if (p.a_sym_kb > 0) { prefetch_tmap(&tm_at_hi); prefetch_tmap(&tm_at_lo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -422,7 +427,13 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
           const int n_base = nb * BLOCK_N + (PAIR ? (int)crank * B_ROWS : 0);
           if (!PAIR) {
             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-            if (!p.a_mn) {
+            if (p.a_sym_kb > 0 && kb >= p.a_sym_kb) {      // second half of (A + A^T).B: the same square array read M-contiguous
+#pragma unroll
+              for (int j = 0; j < BLOCK_M / 64; ++j) {
+                tma_load_2d(&tm_at_hi, &full_bar[stage], sa_hi + j * 8192, mt * BLOCK_M + j * 64, (kb - p.a_sym_kb) * BLOCK_K);
+                tma_load_2d(&tm_at_lo, &full_bar[stage], sa_lo + j * 8192, mt * BLOCK_M + j * 64, (kb - p.a_sym_kb) * BLOCK_K);
+              }
+            } else if (!p.a_mn) {
               tma_load_2d(&tm_a_hi, &full_bar[stage], sa_hi, kb * BLOCK_K, mt * BLOCK_M);
               tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo, kb * BLOCK_K, mt * BLOCK_M);
             } else {
@@ -432,14 +443,15 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
                 tma_load_2d(&tm_a_lo, &full_bar[stage], sa_lo + j * 8192, mt * BLOCK_M + j * 64, kb * BLOCK_K);
               }
             }
+            const int kbb = (p.a_sym_kb > 0 && kb >= p.a_sym_kb) ? kb - p.a_sym_kb : kb;   // B's k block
             if (!p.b_mn) {
-              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kb * BLOCK_K, n_base);
-              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kb * BLOCK_K, n_base);
+              tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi, kbb * BLOCK_K, n_base);
+              tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo, kbb * BLOCK_K, n_base);
             } else {
 #pragma unroll
               for (int j = 0; j < B_ROWS / 64; ++j) {
-                tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, n_base + j * 64, kb * BLOCK_K);
-                tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, n_base + j * 64, kb * BLOCK_K);
+                tma_load_2d(&tm_b_hi, &full_bar[stage], sb_hi + j * 8192, n_base + j * 64, kbb * BLOCK_K);
+                tma_load_2d(&tm_b_lo, &full_bar[stage], sb_lo + j * 8192, n_base + j * 64, kbb * BLOCK_K);
               }
             }
           } else {
@@ -473,7 +485,8 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && crank == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0, PAIR ? 2 * BLOCK_M : BLOCK_M);
+      const uint32_t idesc_n = make_idesc(BLOCK_N, p.a_mn != 0, p.b_mn != 0, PAIR ? 2 * BLOCK_M : BLOCK_M);
+      const uint32_t idesc_t = make_idesc(BLOCK_N, true, p.b_mn != 0, PAIR ? 2 * BLOCK_M : BLOCK_M);   // A read MN-major (A^T half)
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int mb, nb, kb0, kb1;
@@ -487,8 +500,10 @@ __global__ void __launch_bounds__(tc_threads(EPI == EPI_DECODE ? kEwDecode : kEw
           tc_fence_after();
           const uint32_t sa_hi = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sa_lo = sa_hi + A_TILE, sb_hi = sa_lo + A_TILE, sb_lo = sb_hi + B_TILE;
-          const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-          const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;  // bytes per UMMA_K
+          const bool a_t = (p.a_sym_kb > 0 && kb >= p.a_sym_kb) || p.a_mn;                 // this k-block's A tile is MN-major
+          const uint32_t idesc = (p.a_sym_kb > 0 && kb >= p.a_sym_kb) ? idesc_t : idesc_n;
+          const uint32_t a_lbo = a_t ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+          const uint32_t a_step = a_t ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;  // bytes per UMMA_K
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da_hi = make_desc(sa_hi + k * a_step, a_lbo, 1024);
@@ -827,8 +842,9 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;
   // K-major: tensor [rows=MN x cols=K], box {64 k, tile rows};  MN-major: tensor [rows=K x cols=MN], box {64 mn, 64 k}
   if (!A.mn_major) {
-    if ((rc = make_map(&ta_hi, A.hi, p.K, p.M, A.ld, BLOCK_M))) return rc;
-    if ((rc = make_map(&ta_lo, A.lo, p.K, p.M, A.ld, BLOCK_M))) return rc;
+    const uint64_t a_cols = p.a_sym_kb > 0 ? (uint64_t)p.M : (uint64_t)p.K;   // (A + A^T).B: A is M x M, K = 2 x (padded M)
+    if ((rc = make_map(&ta_hi, A.hi, a_cols, p.M, A.ld, BLOCK_M))) return rc;
+    if ((rc = make_map(&ta_lo, A.lo, a_cols, p.M, A.ld, BLOCK_M))) return rc;
   } else {
     if ((rc = make_map(&ta_hi, A.hi, p.M, p.K, A.ld, 64))) return rc;
     if ((rc = make_map(&ta_lo, A.lo, p.M, p.K, A.ld, 64))) return rc;
@@ -837,10 +853,17 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
     if ((rc = make_map(&tb_hi, B.hi, p.K, p.N, B.ld, B_ROWS))) return rc;
     if ((rc = make_map(&tb_lo, B.lo, p.K, p.N, B.ld, B_ROWS))) return rc;
   } else {
-    if ((rc = make_map(&tb_hi, B.hi, p.N, p.K, B.ld, 64))) return rc;
-    if ((rc = make_map(&tb_lo, B.lo, p.N, p.K, B.ld, 64))) return rc;
+    const uint64_t b_rows = p.a_sym_kb > 0 ? (uint64_t)p.M : (uint64_t)p.K;
+    if ((rc = make_map(&tb_hi, B.hi, p.N, b_rows, B.ld, 64))) return rc;
+    if ((rc = make_map(&tb_lo, B.lo, p.N, b_rows, B.ld, 64))) return rc;
   }
   p.a_mn = A.mn_major; p.b_mn = B.mn_major;
+  CUtensorMap tat_hi = ta_hi, tat_lo = ta_lo;
+  if (p.a_sym_kb > 0) {   // A is a square [M x M] array read K-major above; these are its M-contiguous (transposed) views
+    if (PAIR || A.mn_major) { set_error("dae_gemm_sym_bf16x3: unsupported configuration"); return DAE_ERR_UNSUPPORTED; }
+    if ((rc = make_map(&tat_hi, A.hi, p.M, p.M, A.ld, 64))) return rc;
+    if ((rc = make_map(&tat_lo, A.lo, p.M, p.M, A.ld, 64))) return rc;
+  }
   constexpr int smem = STAGES * (2 * BLOCK_M * BLOCK_K * 2 + 2 * B_ROWS * BLOCK_K * 2) + 1024;
   constexpr int threads = tc_threads(EPI == EPI_DECODE ? kEwDecode : kEwStore);
   int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -862,7 +885,7 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
     n = items < slots ? items : slots;
   }
   if (!PAIR) {
-    kern<<<n, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+    kern<<<n, threads, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, tat_hi, tat_lo, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * n); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -870,7 +893,7 @@ static int launch_gemm(const Operand& A, const Operand& B, GemmParams p, cudaStr
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    DAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, p));
+    DAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, tat_hi, tat_lo, p));
   }
   return DAE_OK;
 }
@@ -959,6 +982,27 @@ extern "C" int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, con
   else rc = launch_gemm<256, 2, EPI_STORE, 0, 0, 0>(A, B, p, st);
   if (rc) return rc;
   DAE_CHECK_LAUNCH("dae_gemm_bf16x3");
+  return DAE_OK;
+}
+
+// C[m, n] (+)= alpha * sum_k (G[m, k] + G[k, m]) * B[k, n] for a square G [M x M] (bf16 hi / lo, row-major, ld = ldg) and B stored
+// [M x ldb] row-major (n contiguous).  ONE launch: the k loop runs over G's columns and then over G's rows (the same array through
+// an M-contiguous tensor map), so G + G^T is never formed.  dE2 = alpha (G + G^T) E of the batch_all / batch_hard backward.
+extern "C" int dae_gemm_sym_bf16x3(int32_t M, int32_t N, float alpha, const void* g_hi, const void* g_lo, int64_t ldg, const void* b_hi,
+                                   const void* b_lo, int64_t ldb, float* C, int64_t ldc, int32_t accumulate, void* stream) {
+  DAE_REQUIRE(g_hi && g_lo && b_hi && b_lo && C && M > 0 && N > 0, "dae_gemm_sym_bf16x3: bad arguments");
+  DAE_REQUIRE(ldg % 8 == 0 && ldb % 8 == 0 && ldg >= M && ldb >= N, "dae_gemm_sym_bf16x3: leading dimensions must be multiples of 8 and cover the matrices");
+  DAE_REQUIRE(((uintptr_t)g_hi | (uintptr_t)g_lo | (uintptr_t)b_hi | (uintptr_t)b_lo) % 16 == 0, "dae_gemm_sym_bf16x3: operands must be 16-byte aligned");
+  GemmParams p{};
+  const int kb_half = (M + BLOCK_K - 1) / BLOCK_K;
+  // stream-K: 28 tiles of 128 x 128 at B = 800 would leave 120 SMs idle for a 26-k-block main loop; ~6 k-blocks per CTA instead
+  p.M = M; p.N = N; p.K = 2 * kb_half * BLOCK_K; p.k_splits = 1; p.stream_k = 1; p.atomic = 1; p.alpha = alpha;
+  p.C = C; p.ldc = ldc; p.n_store = N; p.special_col = -1; p.special_out = nullptr; p.a_sym_kb = kb_half;
+  if (!accumulate) DAE_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, (cudaStream_t)stream));
+  Operand A{g_hi, g_lo, ldg, 0}, B{b_hi, b_lo, ldb, 1};
+  int rc = launch_gemm<128, 3, EPI_STORE, 0, 0, 0>(A, B, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  DAE_CHECK_LAUNCH("dae_gemm_sym_bf16x3");
   return DAE_OK;
 }
 

@@ -9,6 +9,7 @@
 // [lo,hi) \ {i} and the negatives the rest.  One CTA per anchor sweeps the n_pos x n_neg rectangle in registers:
 //   softplus(S_ik - S_ij) = log(1 + u_j v_k),  u_j = exp(m - S_ij), v_k = exp(S_ik - m)   (one FFMA + 2 MUFU per triplet)
 // The sweep is bound by the MUFU pipe (lg2 + rcp per triplet), not by HBM or tensor throughput.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace dae {
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
                                                                          const int32_t* __restrict__ seg_lo,
                                                                          const int32_t* __restrict__ seg_hi, float* __restrict__ G,
                                                                          int64_t ldg, double* __restrict__ stats, int Pj_max, int Pk_max,
-                                                                         int pos_only) {
+                                                                         int pos_only, __nv_bfloat16* __restrict__ g_hi,
+                                                                         __nv_bfloat16* __restrict__ g_lo, int64_t ld_split) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_f[32];
   __shared__ double red_d[32];
@@ -192,7 +194,10 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
   float* grow = G + (int64_t)i * ldg;
 
   if (nj <= 1 || nk == 0) {  // no valid triplet with this anchor
-    for (int c = tid; c < B; c += kTripThreads) grow[c] = 0.0f;
+    for (int c = tid; c < B; c += kTripThreads) {
+      grow[c] = 0.0f;
+      if (g_hi) { g_hi[(int64_t)i * ld_split + c] = __float2bfloat16_rn(0.0f); g_lo[(int64_t)i * ld_split + c] = __float2bfloat16_rn(0.0f); }
+    }
     return;
   }
   // the row's value range picks the evaluation tier
@@ -256,6 +261,11 @@ __global__ void __launch_bounds__(kTripThreads) triplet_batch_all_kernel(const f
       g = t * inv;                // +sum_j sigma(S_ik - S_ij)
     }
     grow[c] = g;
+    if (g_hi) {   // the bf16 hi / lo operand copy the (G + G^T).E GEMM reads (no separate split pass)
+      const __nv_bfloat16 h = __float2bfloat16_rn(g);
+      g_hi[(int64_t)i * ld_split + c] = h;
+      g_lo[(int64_t)i * ld_split + c] = __float2bfloat16_rn(g - __bfloat162float(h));
+    }
   }
   const double lsum = block_sum((double)lacc * (double)kLn2, red_d);
   const double psum = block_sum((double)npos, red_d);
@@ -398,9 +408,10 @@ __global__ void triplet_explicit_kernel(const float* __restrict__ E, const float
 }  // namespace dae
 
 extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, const int32_t* seg_lo, const int32_t* seg_hi, float* G,
-                                     int64_t ldg, double* stats, int32_t pos_only, void* stream) {
+                                     int64_t ldg, double* stats, int32_t pos_only, void* g_hi, void* g_lo, int64_t ld_split, void* stream) {
   using namespace dae;
   DAE_REQUIRE(S && seg_lo && seg_hi && G && stats && B >= 1 && B <= 4096 && lds >= B && ldg >= B, "dae_triplet_batch_all: bad arguments");
+  DAE_REQUIRE(!g_hi || (g_lo && ld_split >= B), "dae_triplet_batch_all: bad split outputs");
   cudaStream_t st = (cudaStream_t)stream;
   const int Pj = (B + kJTile - 1) / kJTile * kJTile;
   const int Pk = (B + kKTile - 1) / kKTile * kKTile;
@@ -415,7 +426,8 @@ extern "C" int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, con
       if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
     }
   }
-  triplet_batch_all_kernel<<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk, pos_only);
+  triplet_batch_all_kernel<<<B, kTripThreads, smem, st>>>(S, lds, B, seg_lo, seg_hi, G, ldg, stats, Pj, Pk, pos_only, (__nv_bfloat16*)g_hi,
+                                                          (__nv_bfloat16*)g_lo, ld_split);
   DAE_CHECK_LAUNCH("dae_triplet_batch_all");
   return DAE_OK;
 }

@@ -593,16 +593,16 @@ class TrainEngine:
             E, d, Bx = self.E, self.dE, explicit_B
             self._k('dae_triplet_explicit', ptr(E[0:Bx]), ptr(E[Bx:2 * Bx]), ptr(E[2 * Bx:3 * Bx]), Bx, H, H, self.alpha, ptr(d[0:Bx]),
                     ptr(d[Bx:2 * Bx]), ptr(d[2 * Bx:3 * Bx]), ptr(self.stats), main.cuda_stream)
+        if par:
+            self._fork(main, sideB)           # branch B: after the zeroing (already on sideB) and once dE owns the SMs; it needs
+            with torch.cuda.stream(sideB):    # nothing from the mining branch, so it does not wait for it
+                self._dW_gemm(B, accumulate=1)
         if strat in (1, 2):  # dE += alpha (G + G^T) E: on the tensor-core path the product already sits in dE2 (mining branch)
             if ev_mined is not None:
                 main.wait_event(ev_mined)
             if not tc:
                 self._gemm(B, H, B, self.alpha, self.G, B, 1, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
                 self._gemm(B, H, B, self.alpha, self.G, 1, B, self.E, 1, H, 1.0, self.dE, H, tag='gemm_dE_tri')
-        if par:
-            self._fork(main, sideB)           # branch B: after the zeroing (already on sideB) and after dE / dE_tri were issued
-            with torch.cuda.stream(sideB):
-                self._dW_gemm(B, accumulate=1)
         if par and gather:
             main.wait_event(ev_scan)
         self._encode_backward(B, rows, dE_add=self.dE2 if (tc and strat in (1, 2)) else None, dbh_zeroed=1 if par else 0)
@@ -626,7 +626,11 @@ class TrainEngine:
     def _dE_triplet(self, B, stream):
         """dE2 = alpha (G + G^T) E, the triplet part of dL/dE; the encode backward adds it to the decode part (dE_add)."""
         with torch.cuda.stream(stream):
-            if self.small_gemm == 'tc':
+            if self.small_gemm == 'tc' and self.strategy == 1:
+                # batch_all: the sweep wrote G as bf16 hi / lo; ONE GEMM walks G's columns and then its rows: alpha (G + G^T) E
+                self._k('dae_gemm_sym_bf16x3', B, self.H, float(self.alpha), ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
+                        ptr(self.E_hi), ptr(self.E_lo), self.E_hi.stride(0), ptr(self.dE2), self.H, 0, stream.cuda_stream, tag='gemm_dE_tri')
+            elif self.small_gemm == 'tc':
                 self._k('dae_sym_split_bf16', ptr(self.G), B, B, self.alpha, ptr(self.GG_hi), ptr(self.GG_lo), self.GG_hi.stride(0),
                         stream.cuda_stream)
                 self._tc_gemm(B, self.H, B, 1.0, (self.GG_hi, self.GG_lo), 0, (self.E_hi, self.E_lo), 1, self.dE2, self.H, tag='gemm_dE_tri')
@@ -654,8 +658,10 @@ class TrainEngine:
         else:
             self._gemm(B, B, H, 1.0, self.E, H, 1, self.E, H, 1, 0.0, self.S, B, tag='gemm_gram')  # S = E.E^T
         if strat == 1:
+            # G also leaves as the bf16 hi / lo pair the (G + G^T).E GEMM reads
             self._k('dae_triplet_batch_all', ptr(self.S), B, B, ptr(self.seg_lo), ptr(self.seg_hi), ptr(self.G), B,
-                    ptr(self.stats), 0, st)
+                    ptr(self.stats), 0, ptr(self.GG_hi) if tc else None, ptr(self.GG_lo) if tc else None,
+                    self.GG_hi.stride(0) if tc else 0, st)
         else:
             self._k('dae_triplet_batch_hard', ptr(self.S), B, B, ptr(self.labels_b), ptr(self.G), B, ptr(self.weight),
                     ptr(self.stats), st, n_launch=2)

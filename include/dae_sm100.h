@@ -189,6 +189,12 @@ int dae_gemm_bf16x3(int32_t M, int32_t N, int32_t K, float alpha, const void* a_
                     int64_t lda, int32_t a_mn_major, const void* b_hi, const void* b_lo, int64_t ldb,
                     int32_t b_mn_major, float* C, int64_t ldc, int32_t n_store, int32_t special_col,
                     float* special_out, int32_t k_splits, int32_t accumulate, void* stream);
+/* C[m,n] (+)= alpha * sum_k (G[m,k] + G[k,m]) * B[k,n] for a square G [M x M] (bf16 hi/lo, row-major) and B stored [M x ldb] row-major:
+ * dE2 = alpha (G + G^T) E of the triplet backward in ONE launch -- the k loop runs over G's columns and then over G's rows (the same
+ * array through an M-contiguous tensor map), so G + G^T is never formed.  Stream-K with fp32 atomics; C is zeroed first unless accumulate. */
+int dae_gemm_sym_bf16x3(int32_t M, int32_t N, float alpha, const void* g_hi, const void* g_lo, int64_t ldg,
+                        const void* b_hi, const void* b_lo, int64_t ldb, float* C, int64_t ldc, int32_t accumulate,
+                        void* stream);
 /* Tile engine selection of the two entry points above (test hook).  pair_mode: -1 = CTA pairs (cta_group::2: two SMs share one
  * 256-row UMMA tile, each staging half of the B operand) for the large store GEMMs only -- the default --, 0 = never, 1 = whenever
  * possible (fused decode included).  lean: 0 (default) = deepest operand rings; 1 = 2-stage rings (128 KB per CTA), which leave
@@ -229,10 +235,12 @@ int dae_colsum(const float* M, int32_t n_rows, int32_t n_cols, int64_t ld, float
  *   Writes G (B x B): dL_tri/dS, accumulates loss sum / positive count into stats.
  *   pos_only != 0 (pos_triplets_only=True, :118-120; never used by the model): the loss sum covers positive triplets
  *   only and G receives raw COUNTS of positive triplets (G[i,j] = -#k, G[i,k] = +#j) from which the caller derives the weights.
+ *   g_hi / g_lo (optional, bf16 [B x ld_split]): G also leaves as the hi / lo operand pair dae_gemm_sym_bf16x3 reads.
  * batch_hard (triplet_loss_utils.py:202-259): also writes the data weight (w) and sum_w.
  */
 int dae_triplet_batch_all(const float* S, int64_t lds, int32_t B, const int32_t* seg_lo, const int32_t* seg_hi,
-                          float* G, int64_t ldg, double* stats, int32_t pos_only, void* stream);
+                          float* G, int64_t ldg, double* stats, int32_t pos_only, void* g_hi, void* g_lo,
+                          int64_t ld_split, void* stream);
 int dae_triplet_batch_hard(const float* S, int64_t lds, int32_t B, const float* labels, float* G, int64_t ldg,
                            float* weight, double* stats, void* stream);
 /* explicit triplets (autoencoder_triplet.py:308-311): loss = mean softplus(e.en - e.ep); ACCUMULATES alpha * dloss

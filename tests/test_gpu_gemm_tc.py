@@ -101,6 +101,30 @@ def test_gemm_stream_k(M, N, K, a_mn, b_mn):
     assert rel_err(C2.cpu().numpy(), 1.0 + 2.0 * want) < 2e-5
 
 
+@pytest.mark.parametrize('M,N', [(800, 500), (130, 52), (64, 100), (333, 24)])
+def test_gemm_sym_is_g_plus_gt_times_b(M, N):
+    """dae_gemm_sym_bf16x3: C = alpha (G + G^T) B in one launch (k loop over G's columns, then over its rows), with and without
+    accumulation, ragged sizes (M not a multiple of the 64-wide k block)."""
+    from dae_rnn_news_recommendation_b200 import _cabi
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N)
+    G = torch.randn(M, M, device=DEV, generator=g)
+    Bm = torch.randn(M, N, device=DEV, generator=g)
+    pad = lambda n: (n + 7) // 8 * 8
+    Ghl, Bhl = _split(G, pad(M)), _split(Bm, pad(N))
+    want = ((G.double() + G.double().t()) @ Bm.double()).cpu().numpy()
+    st = torch.cuda.current_stream().cuda_stream
+    C = torch.full((M, N), float('nan'), device=DEV)
+    _cabi.call('dae_gemm_sym_bf16x3', M, N, 0.5, Ghl[0].data_ptr(), Ghl[1].data_ptr(), pad(M), Bhl[0].data_ptr(), Bhl[1].data_ptr(), pad(N),
+               C.data_ptr(), N, 0, st)
+    torch.cuda.synchronize()
+    assert rel_err(C.cpu().numpy(), 0.5 * want) < 2e-5
+    C2 = torch.ones(M, N, device=DEV)
+    _cabi.call('dae_gemm_sym_bf16x3', M, N, 1.0, Ghl[0].data_ptr(), Ghl[1].data_ptr(), pad(M), Bhl[0].data_ptr(), Bhl[1].data_ptr(), pad(N),
+               C2.data_ptr(), N, 1, st)
+    torch.cuda.synchronize()
+    assert rel_err(C2.cpu().numpy(), 1.0 + want) < 2e-5
+
+
 @pytest.mark.parametrize('loss,dec,zscale', [('cross_entropy', 'sigmoid', 1.0), ('cross_entropy', 'sigmoid', 12.0), ('mean_squared', 'none', 1.0),
                                              ('mean_squared', 'tanh', 1.0), ('mean_squared', 'sigmoid', 1.0)])
 def test_fused_decode_matches_unfused(loss, dec, zscale):
