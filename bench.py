@@ -441,7 +441,7 @@ def main():
             dist.all_reduce(tme, op=dist.ReduceOp.MAX)
         e2e_val = Ke * B * world / (float(tme.item()) * 1e-3)
         e2e_api = ('TrainEngine.run_feeds(HostFeeds): per step a pinned host batch -> H2D (copy stream, overlapping the previous step) -> '
-                   'step -> async D2H of the scalars; one host sync after the last step')
+                   'step (the next batch\'s label sort staged on a side branch) -> async D2H of the scalars; one host sync after the last step')
     h2d = int(np.mean([f.nbytes for f in feeds[2:]]))
 
     # -- roofline table (every kernel of the step) and the longest kernel's entry

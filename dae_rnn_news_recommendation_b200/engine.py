@@ -150,6 +150,8 @@ class TrainEngine:
         self.timed = None  # {kernel name: [(start_event, end_event), ...]} when per-kernel timing is on
         self._feed_dev = None
         self._feed_graph = None
+        self._feed_graph_staged = None
+        self._labels_next = None
         self._graph2 = None
         self._ctl_owner = None
         self._stats_host = torch.empty(STAT_SLOTS, dtype=torch.float64).pin_memory()
@@ -239,10 +241,11 @@ class TrainEngine:
         return {k: float(s[i]) for k, i in STAT.items()}
 
     def run_feeds(self, feeds):
-        """A stream of host feeds (same layout: built with one `cap_nnz`), the input pipeline of a training loop: feed i+1's
-        H2D copy runs on a copy stream while step i computes (two device staging buffers), every step's scalars leave through an
-        asynchronous D2H copy into a pinned ring, and the host synchronises once, after the last step.  Returns the list of per-step
-        stats dicts (identical to calling run_feed on each feed in turn)."""
+        """A stream of host feeds (same layout: built with one `cap_nnz`), the input pipeline of a training loop: the H2D copies of the
+        next two feeds run on a copy stream while step i computes (three device staging buffers), the triplet strategies prepare feed
+        i+1's batch (label sort, segments, weights) on a side branch of step i, every step's scalars leave through an asynchronous
+        D2H copy into a pinned ring, and the host synchronises once, after the last step.  Returns the list of per-step stats dicts
+        (identical to calling run_feed on each feed in turn)."""
         feeds = list(feeds)
         if not feeds:
             return []
@@ -253,33 +256,63 @@ class TrainEngine:
         n = len(feeds) - 1
         if n == 0:
             return out
-        if getattr(self, '_feed_stage', None) is None or self._feed_stage[0].numel() < f0.nbytes:
-            self._feed_stage = [torch.empty(self._feed_dev.numel(), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        if self._feed_graph is None:         # graph replay disabled (DAE_CUDA_GRAPH=0): plain per-feed calls
+            return out + [self.run_feed(f) for f in feeds[1:]]
+        NS = 3                               # device staging buffers: feed j+2 is in flight while step j runs
+        if getattr(self, '_feed_stage', None) is None or len(self._feed_stage) != NS or self._feed_stage[0].numel() < f0.nbytes:
+            self._feed_stage = [torch.empty(self._feed_dev.numel(), dtype=torch.uint8, device=self.device) for _ in range(NS)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
+        B, nb = f0.B, f0.nbytes
+        # triplet strategies: the label sort / class segments / data weights of feed j+1 (dae_batch_prepare_next, one CTA, ~20 us) are
+        # computed on a side branch of step j from the next feed's labels, which are already on the device; step j+1 starts with
+        # the copy-out dae_batch_commit instead.  The streamed loop gets its own captured graph for that.
+        staged = self.strategy in (1, 2) and f0.has_labels
+        if staged:
+            key = self._feed_graph               # (re-captured whenever the plain feed graph is: same buffers, same layout)
+            if self._feed_graph_staged is None or self._feed_graph_staged[0] is not key:
+                self._feed_labels_next = self.labels.clone()
+                saved = (self._graph, self._graph2, getattr(self, '_graph_meta', None))
+                self._labels_next = self._feed_labels_next
+                try:
+                    g = self.capture_step_graph(None, B, None, row_stride=0, staged='feed')
+                finally:
+                    self._labels_next = None
+                self._feed_graph_staged = (key, g, self._graph2)
+                self._graph, self._graph2, self._graph_meta = saved
+            graph = self._feed_graph_staged
+        else:
+            graph = self._feed_graph
         ring = torch.empty(n, STAT_SLOTS, dtype=torch.float64).pin_memory()
         main, cs = torch.cuda.current_stream(), self._copy_stream
-        ev_copy = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_used = [None, None]
-        nb = f0.nbytes
+        ev_copy = [torch.cuda.Event() for _ in range(NS)]
+        ev_used = [None] * NS
 
-        def issue_copy(i):
-            k = i & 1
+        def issue_copy(j):                   # feed j (1..n) -> staging buffer j % NS
+            k = j % NS
             if ev_used[k] is not None:
                 cs.wait_event(ev_used[k])        # the staging buffer's previous content has been consumed
             with torch.cuda.stream(cs):
-                self._feed_stage[k][:nb].copy_(feeds[i + 1].host, non_blocking=True)
+                self._feed_stage[k][:nb].copy_(feeds[j].host, non_blocking=True)
                 ev_copy[k].record(cs)
-        issue_copy(0)
-        for i in range(n):
-            k = i & 1
-            if i + 1 < n:
-                issue_copy(i + 1)
+        for j in range(1, min(n, NS - 1) + 1):
+            issue_copy(j)
+        for j in range(1, n + 1):
+            k = j % NS
+            if j + NS - 1 <= n:
+                issue_copy(j + NS - 1)           # reuses the buffer of feed j-1, consumed one iteration ago
             main.wait_event(ev_copy[k])
             self._feed_dev[:nb].copy_(self._feed_stage[k][:nb], non_blocking=True)      # device-to-device, into the graph's buffer
+            if staged:
+                if j == 1:
+                    self.stage_batch(None, 0, B)     # the first streamed step's batch; every later one is staged by the step before
+                if j < n:                            # labels of feed j+1 (its H2D copy was issued a whole step ago)
+                    k1 = (j + 1) % NS
+                    main.wait_event(ev_copy[k1])
+                    self._feed_labels_next.copy_(self._feed_stage[k1][f0.off_labels:f0.off_labels + 4 * B].view(torch.float32), non_blocking=True)
             ev_used[k] = torch.cuda.Event()
             ev_used[k].record(main)
-            self._replay(self._feed_graph[1], self._feed_graph[2])
-            ring[i].copy_(self.stats, non_blocking=True)
+            self._replay(graph[1], graph[2])
+            ring[j - 1].copy_(self.stats, non_blocking=True)
         main.synchronize()
         r = ring.numpy()
         out.extend({k: float(r[i, j]) for k, j in STAT.items()} for i in range(n))
@@ -461,7 +494,8 @@ class TrainEngine:
 
     def _stage_next_batch(self, perm, staged, B, stream):
         n_perm, stride = staged
-        self._k('dae_batch_prepare_next', ptr(perm), int(n_perm), int(stride), ptr(self._ctl), B, ptr(self.labels), self.strategy,
+        labels = self.labels if self._labels_next is None else self._labels_next    # (run_feeds: the NEXT feed's labels)
+        self._k('dae_batch_prepare_next', ptr(perm), int(n_perm), int(stride), ptr(self._ctl), B, ptr(labels), self.strategy,
                 *[ptr(t) for t in self._stage], stream.cuda_stream)
 
     def stage_batch(self, perm, offset, B):
@@ -851,8 +885,9 @@ class TrainEngine:
         stride = int(B if row_stride is None else row_stride)
         saved = (self.step_count, self.timed)
         self.timed = None
-        n_perm = int(perm_buf.numel()) if perm_buf is not None else 0
-        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and perm_buf is not None
+        feed = staged == 'feed'       # run_feeds: rows 0..B-1 of the feed buffer, the next batch's labels in self._labels_next
+        n_perm = int(perm_buf.numel()) if perm_buf is not None else (B if feed else 0)
+        use_stage = bool(staged) and explicit_n is None and self.strategy in (1, 2) and (perm_buf is not None or feed)
         self._graph_meta = {'perm': perm_buf, 'B': B, 'staged': use_stage}
 
         def one_step():

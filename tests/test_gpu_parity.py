@@ -275,7 +275,7 @@ def test_host_feed_graph_replay_matches_eager(gemm_mode, monkeypatch):
     """TrainEngine.run_feed (the session.run(feed_dict) analogue): feeds with a common cap_nnz are replayed from one captured
     graph and give the same trajectory as eager per-feed launches."""
     from dae_rnn_news_recommendation_b200.engine import HostFeed
-    F, H, B, steps = 400, 32, 64, 4
+    F, H, B, steps = 400, 32, 64, 7
     rng = np.random.default_rng(71)
     W0 = xavier(F, H, 72) * 3
     batches = []
