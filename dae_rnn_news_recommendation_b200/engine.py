@@ -150,7 +150,7 @@ class TrainEngine:
         self.timed = None  # {kernel name: [(start_event, end_event), ...]} when per-kernel timing is on
         self._feed_dev = None
         self._feed_graph = None
-        self._feed_graph_staged = None
+        self._feed_stream = None
         self._labels_next = None
         self._graph2 = None
         self._ctl_owner = None
@@ -211,12 +211,7 @@ class TrainEngine:
         key = (B, nnz, feed.has_labels, feed.F)
         fixed = feed.cap_nnz is not None and os.environ.get('DAE_CUDA_GRAPH', '1') == '1'
         if not (fixed and self._feed_graph is not None and self._feed_graph[0] == key):
-            v = lambda off, nb, dt: d[off:off + nb].view(dt)
-            csr = _CSRView(v(feed.off_indptr, 8 * (B + 1), torch.int64), v(feed.off_indices, 4 * nnz, torch.int32),
-                           v(feed.off_values, 4 * nnz, torch.float32), (B, feed.F))
-            self.csr = self.csr_c = csr
-            self.values_c = v(feed.off_values_c, 4 * nnz, torch.float32)
-            self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
+            self._feed_bind(feed)
             if fixed:   # capture the step on this layout (restores the parameters after its warm-up steps)
                 saved = (self._graph, self._graph2, getattr(self, '_graph_meta', None))
                 if self.strategy == 3:   # explicit triplets: the feed holds the stacked [org; pos; neg] rows of the batch
@@ -240,79 +235,110 @@ class TrainEngine:
         s = self._stats_host.numpy()
         return {k: float(s[i]) for k, i in STAT.items()}
 
+    def _feed_bind(self, feed, buf=None):
+        """Point the engine's batch views (CSR, corrupted values, labels) at the feed layout inside `buf` (default: run_feed's buffer)."""
+        d, B, nnz = (self._feed_dev if buf is None else buf), feed.B, feed.nnz
+        v = lambda off, nb, dt: d[off:off + nb].view(dt)
+        self.csr = self.csr_c = _CSRView(v(feed.off_indptr, 8 * (B + 1), torch.int64), v(feed.off_indices, 4 * nnz, torch.int32),
+                                         v(feed.off_values, 4 * nnz, torch.float32), (B, feed.F))
+        self.values_c = v(feed.off_values_c, 4 * nnz, torch.float32)
+        self.labels = v(feed.off_labels, 4 * B, torch.float32) if feed.has_labels else None
+
     def run_feeds(self, feeds):
         """A stream of host feeds (same layout: built with one `cap_nnz`), the input pipeline of a training loop: the H2D copies of the
-        next two feeds run on a copy stream while step i computes (three device staging buffers), the triplet strategies prepare feed
-        i+1's batch (label sort, segments, weights) on a side branch of step i, every step's scalars leave through an asynchronous
-        D2H copy into a pinned ring, and the host synchronises once, after the last step.  Returns the list of per-step stats dicts
-        (identical to calling run_feed on each feed in turn)."""
+        next two feeds run on a copy stream while step i computes (three device feed buffers, one captured graph each), the triplet
+        strategies prepare feed i+1's batch (label sort, segments, weights) on a side branch of step i, every step's scalars leave
+        through an asynchronous D2H copy into a pinned ring, and the host synchronises once, after the last step.  Returns the list
+        of per-step stats dicts (identical to calling run_feed on each feed in turn)."""
         feeds = list(feeds)
         if not feeds:
             return []
         f0 = feeds[0]
         assert all(f.cap_nnz is not None and (f.B, f.nnz, f.has_labels, f.F, f.nbytes) == (f0.B, f0.nnz, f0.has_labels, f0.F, f0.nbytes)
                    for f in feeds), 'run_feeds needs feeds of one common layout (HostFeed(..., cap_nnz=...))'
-        out = [self.run_feed(f0)]            # captures the step on this layout if it has not been yet
-        n = len(feeds) - 1
+        key = (f0.B, f0.nnz, f0.has_labels, f0.F)
+        out = []
+        if not (self._feed_graph is not None and self._feed_graph[0] == key and self._feed_dev.numel() >= f0.nbytes):
+            out.append(self.run_feed(f0))    # first use of this layout: captures the step on it
+            feeds = feeds[1:]
+        if self._feed_graph is None:         # graph replay disabled (DAE_CUDA_GRAPH=0): plain per-feed calls
+            return out + [self.run_feed(f) for f in feeds]
+        n = len(feeds)
         if n == 0:
             return out
-        if self._feed_graph is None:         # graph replay disabled (DAE_CUDA_GRAPH=0): plain per-feed calls
-            return out + [self.run_feed(f) for f in feeds[1:]]
-        NS = 3                               # device staging buffers: feed j+2 is in flight while step j runs
-        if getattr(self, '_feed_stage', None) is None or len(self._feed_stage) != NS or self._feed_stage[0].numel() < f0.nbytes:
-            self._feed_stage = [torch.empty(self._feed_dev.numel(), dtype=torch.uint8, device=self.device) for _ in range(NS)]
-            self._copy_stream = torch.cuda.Stream(device=self.device)
+        LOG_ROWS = 1024
+        if n > LOG_ROWS:                     # the per-step scalars go through a device log of LOG_ROWS rows
+            for i in range(0, n, LOG_ROWS):
+                out.extend(self.run_feeds(feeds[i:i + LOG_ROWS]))
+            return out
+        # The streamed loop owns NS = 3 device feed buffers and ONE CAPTURED GRAPH PER BUFFER (the step reads its batch where the H2D
+        # copy put it: no device-to-device hop), each writing its scalars into row ctl[1] of a device log.  Step j replays graph
+        # j % 3; the H2D copy of feed j+2 runs on the copy stream meanwhile, and so does the D2H copy of step j-1's log row.  Triplet
+        # strategies: graph k prepares the NEXT batch (label sort / class segments / data weights, dae_batch_prepare_next, one CTA,
+        # ~20 us) on a side branch from the labels inside buffer (k+1) % 3, and starts with the copy-out dae_batch_commit.
+        NS = 3
         B, nb = f0.B, f0.nbytes
-        # triplet strategies: the label sort / class segments / data weights of feed j+1 (dae_batch_prepare_next, one CTA, ~20 us) are
-        # computed on a side branch of step j from the next feed's labels, which are already on the device; step j+1 starts with
-        # the copy-out dae_batch_commit instead.  The streamed loop gets its own captured graph for that.
         staged = self.strategy in (1, 2) and f0.has_labels
-        if staged:
-            key = self._feed_graph               # (re-captured whenever the plain feed graph is: same buffers, same layout)
-            if self._feed_graph_staged is None or self._feed_graph_staged[0] is not key:
-                self._feed_labels_next = self.labels.clone()
-                saved = (self._graph, self._graph2, getattr(self, '_graph_meta', None))
-                self._labels_next = self._feed_labels_next
-                try:
-                    g = self.capture_step_graph(None, B, None, row_stride=0, staged='feed')
-                finally:
-                    self._labels_next = None
-                self._feed_graph_staged = (key, g, self._graph2)
+        st = self._feed_stream
+        if st is None or st['owner'] is not self._feed_graph:
+            bufs = [torch.empty(self._feed_dev.numel(), dtype=torch.uint8, device=self.device) for _ in range(NS)]
+            for bk in bufs:
+                bk[:nb].copy_(self._feed_dev[:nb])       # a valid batch of this layout for the captures' warm-up steps
+            log = torch.zeros(LOG_ROWS, STAT_SLOTS, dtype=torch.float64, device=self.device)
+            saved = (self._graph, self._graph2, getattr(self, '_graph_meta', None))
+            graphs = []
+            try:
+                for k in range(NS):
+                    self._feed_bind(f0, bufs[k])
+                    if staged:
+                        self._labels_next = bufs[(k + 1) % NS][f0.off_labels:f0.off_labels + 4 * B].view(torch.float32)
+                    if self.strategy == 3:
+                        g = self.capture_step_graph(None, B // 3, log, row_stride=0, staged=False, explicit_n=B // 3)
+                    else:
+                        g = self.capture_step_graph(None, B, log, row_stride=0, staged='feed' if staged else False)
+                    graphs.append((g, self._graph2))
+            finally:
+                self._labels_next = None
                 self._graph, self._graph2, self._graph_meta = saved
-            graph = self._feed_graph_staged
-        else:
-            graph = self._feed_graph
-        ring = torch.empty(n, STAT_SLOTS, dtype=torch.float64).pin_memory()
-        main, cs = torch.cuda.current_stream(), self._copy_stream
+                self._feed_bind(f0)
+            st = self._feed_stream = {'owner': self._feed_graph, 'bufs': bufs, 'log': log, 'graphs': graphs,
+                                      'copy_stream': torch.cuda.Stream(device=self.device),
+                                      'ring': torch.empty(LOG_ROWS, STAT_SLOTS, dtype=torch.float64).pin_memory()}
+        bufs, log, graphs, cs, ring = st['bufs'], st['log'], st['graphs'], st['copy_stream'], st['ring']
+        self._set_ctl(0, 0)                  # batch cursor 0 (stride 0), log row 0, optimizer step: continues
+        self._ctl_owner = 'feed'
+        main = torch.cuda.current_stream()
         ev_copy = [torch.cuda.Event() for _ in range(NS)]
-        ev_used = [None] * NS
+        ev_done = [None] * n
 
-        def issue_copy(j):                   # feed j (1..n) -> staging buffer j % NS
-            k = j % NS
-            if ev_used[k] is not None:
-                cs.wait_event(ev_used[k])        # the staging buffer's previous content has been consumed
+        def issue_copy(j):                   # feed j -> buffer j % NS, once step j-3 (its previous reader) and step j-4's label read are done
             with torch.cuda.stream(cs):
-                self._feed_stage[k][:nb].copy_(feeds[j].host, non_blocking=True)
-                ev_copy[k].record(cs)
-        for j in range(1, min(n, NS - 1) + 1):
+                if j >= NS:
+                    cs.wait_event(ev_done[j - NS])
+                bufs[j % NS][:nb].copy_(feeds[j].host, non_blocking=True)
+                ev_copy[j % NS].record(cs)
+        cs.wait_stream(main)                 # (earlier work on the main stream may still read the buffers)
+        for j in range(min(n, NS - 1)):
             issue_copy(j)
-        for j in range(1, n + 1):
+        for j in range(n):
             k = j % NS
-            if j + NS - 1 <= n:
-                issue_copy(j + NS - 1)           # reuses the buffer of feed j-1, consumed one iteration ago
             main.wait_event(ev_copy[k])
-            self._feed_dev[:nb].copy_(self._feed_stage[k][:nb], non_blocking=True)      # device-to-device, into the graph's buffer
             if staged:
-                if j == 1:
-                    self.stage_batch(None, 0, B)     # the first streamed step's batch; every later one is staged by the step before
-                if j < n:                            # labels of feed j+1 (its H2D copy was issued a whole step ago)
-                    k1 = (j + 1) % NS
-                    main.wait_event(ev_copy[k1])
-                    self._feed_labels_next.copy_(self._feed_stage[k1][f0.off_labels:f0.off_labels + 4 * B].view(torch.float32), non_blocking=True)
-            ev_used[k] = torch.cuda.Event()
-            ev_used[k].record(main)
-            self._replay(graph[1], graph[2])
-            ring[j - 1].copy_(self.stats, non_blocking=True)
+                if j == 0:                       # the first step's batch; every later one is staged by the step before it
+                    self._feed_bind(f0, bufs[0])
+                    self.stage_batch(None, 0, B)
+                    self._feed_bind(f0)
+                if j + 1 < n:
+                    main.wait_event(ev_copy[(j + 1) % NS])      # labels of feed j+1 (copy issued a whole step ago)
+            if j + NS - 1 < n:
+                issue_copy(j + NS - 1)           # into the buffer of feed j-1: runs while step j computes
+            self._replay(*graphs[k])
+            ev_done[j] = torch.cuda.Event()
+            ev_done[j].record(main)
+            with torch.cuda.stream(cs):          # D2H of step j's scalars, off the main stream
+                cs.wait_event(ev_done[j])
+                ring[j].copy_(log[j], non_blocking=True)
+        cs.synchronize()
         main.synchronize()
         r = ring.numpy()
         out.extend({k: float(r[i, j]) for k, j in STAT.items()} for i in range(n))
@@ -945,6 +971,12 @@ class TrainEngine:
     def set_step_cursor(self, offset, log_row=0):
         """Host-side (re)positioning of the device cursors, e.g. at an epoch start."""
         self._ctl_owner = 'fit'
+        self._set_ctl(offset, log_row)
+        m = getattr(self, '_graph_meta', None)
+        if m is not None and m['staged']:      # the replayed step takes its batch from the staging buffers
+            self.stage_batch(m['perm'], int(offset), m['B'])
+
+    def _set_ctl(self, offset, log_row):
         if getattr(self, '_ctl_host', None) is None:
             self._ctl_host = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(8)]   # ring: the copies are asynchronous
             self._ctl_host_i = 0
@@ -952,9 +984,6 @@ class TrainEngine:
         self._ctl_host_i += 1
         h[0], h[1], h[2], h[3] = int(offset), int(log_row), self.step_count + 1, 0
         self.ctl.copy_(h, non_blocking=True)
-        m = getattr(self, '_graph_meta', None)
-        if m is not None and m['staged']:      # the replayed step takes its batch from the staging buffers
-            self.stage_batch(m['perm'], int(offset), m['B'])
 
     def replay_step(self):
         self._replay(self._graph, self._graph2)

@@ -295,6 +295,7 @@ def test_host_feed_graph_replay_matches_eager(gemm_mode, monkeypatch):
     # streamed form (the next feed's H2D copy overlaps the current step, scalars through a pinned ring): same trajectory
     eng = _engine(F, H, opt='momentum', learning_rate=0.05, triplet_strategy='batch_all')
     eng.set_parameters(W0)
-    outs = eng.run_feeds([HostFeed(xb, xc, lb, cap_nnz=cap) for xb, xc, lb in batches])
+    feeds = [HostFeed(xb, xc, lb, cap_nnz=cap) for xb, xc, lb in batches]
+    outs = eng.run_feeds(feeds[:3]) + eng.run_feeds(feeds[3:])     # (the second call streams every feed: the layout is captured)
     assert len(outs) == steps and eng.step_count == steps
     assert rel_err([o['cost'] for o in outs], res[1][0]) < 1e-6 and rel_err(eng.get_parameters()['enc_w'], res[1][1]) < 1e-6

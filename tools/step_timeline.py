@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--config', default='C2')
 ap.add_argument('--steps', type=int, default=6)
 ap.add_argument('--rows', type=int, default=20000)
+ap.add_argument('--feeds', action='store_true', help='timeline of TrainEngine.run_feeds (streamed pinned host feeds) instead of device-resident replays')
 a = ap.parse_args()
 w = bench.CONFIGS[a.config]
 dev = torch.device('cuda:0')
@@ -33,9 +34,25 @@ for _ in range(3):
     eng.replay_step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
+feeds = None
+if a.feeds:
+    from dae_rnn_news_recommendation_b200.engine import HostFeed
+    rng = np.random.RandomState(7)
+    batches = []
+    for i in range(a.steps + 2):
+        idx = rng.randint(0, a.rows, B)
+        xb = x[idx]
+        batches.append((xb, xb.data * (rng.rand(xb.nnz) >= w['corr_frac']), labels[idx]))
+    cap = max(b[0].nnz for b in batches)
+    feeds = [HostFeed(xb, xc, lb, cap_nnz=cap) for xb, xc, lb in batches]
+    eng.run_feeds(feeds[:3])
+    torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for _ in range(a.steps):
-        eng.replay_step()
+    if feeds:
+        eng.run_feeds(feeds[1:])
+    else:
+        for _ in range(a.steps):
+            eng.replay_step()
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
@@ -43,6 +60,13 @@ rows = [{'name': e.name[:60], 't0': e.time_range.start, 't1': e.time_range.end, 
 # split into steps at the first kernel of a step (the batch commit / prepare kernel)
 first = [i for i, r in enumerate(rows) if 'batch_commit' in r['name'] or 'batch_rows' in r['name']]
 out = {'config': w['name'], 'n_events': len(rows), 'steps_found': len(first)}
+if rows:
+    out['step_starts_us'] = [round(rows[i]['t0'] - rows[0]['t0'], 1) for i in first]
+    out['span_us'] = round(max(r['t1'] for r in rows) - rows[0]['t0'], 1)
+    out['head'] = [{'name': r['name'][:40], 'start_us': round(r['t0'] - rows[0]['t0'], 1), 'dur_us': round(r['t1'] - r['t0'], 1)} for r in rows[:8]]
+    cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU]
+    if cpu:
+        out['first_gpu_event_after_first_cpu_op_us'] = round(rows[0]['t0'] - min(e.time_range.start for e in cpu), 1)
 if len(first) >= 3:
     lo, hi = first[-2], first[-1]
     step = rows[lo:hi]
